@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""Benchmark of the path-join + permutation-scoring hot path (BASELINE.json metric: path-pair*perm scores / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 3 - synthetic cohort of 10,000 patients (5,000 cases), 15,000 genes, path
+length 4, 1,000 permutations, methods 1 + 2 - on a seeded heavy-tailed signed network (the reference's Rels.dat is not
+in the checkout; sizes generated are reported in `config`).  One step = the whole level schedule 1a,1b,2,3,4 of
+`ProcessPaths` (src/wrapper.cpp:225-269) for method 1 and then method 2.
+
+  value      device-timed throughput with all inputs resident in HBM (packed gene rows, permutation masks, value table)
+  e2e        the same schedule through the reference-facing calls with HOST buffers in the R-facing formats
+             (IntegerMatrix data, CaseORControl int matrix, value table), uploads and result read-back inside the timing
+  roofline   the level-4 join kernel: algorithmic bytes / its CUDA-event time vs the measured HBM peak, plus
+             the integer word-op rate vs the nominal POPC-pipe peak (the kernel is integer-bound, not HBM-bound)
+  cpu_baseline  the reference's own join (oracle/_ref, built from the unmodified reference sources with
+             g++ -O3 -march=<host level> -mpopcnt) on all host cores over a bounded sample of the same level-4 join
+
+Multi-GPU (N > 1): levels 1-3 are computed redundantly per rank (tiny), the level-4 upstream rows are sharded by pair
+count, permutation maxima are merged with ONE NCCL allreduce(max), top-K lists with an all-gather + merge.  Fixed total
+work => "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n_cases=5000, n_ctrls=5000, n_genes=15000, n_edges=60000, n_perms=1000, path_length=4, top_k=10, seed=20261021)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "dense", "sparse"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per method for the baseline sample")
+    for k, v in WORKLOAD.items():
+        ap.add_argument("--" + k.replace("_", "-"), type=type(v), default=v)
+    return ap.parse_args()
+
+
+def make_workload(a):
+    from geneticscre_b200 import synth
+
+    t = time.time()
+    w = synth.make_workload(a.n_cases, a.n_ctrls, a.n_genes, a.n_edges, a.n_perms, a.seed, max_path_length=a.path_length, real_table=True)
+    return w, time.time() - t
+
+
+def workload_config(a, w):
+    lv = w.net.levels
+    return {
+        "workload": "BASELINE config 3: synthetic cohort, methods 1+2, full level schedule 1a,1b,2,3,4 per method",
+        "patients": w.n_patients, "cases": w.n_cases, "genes_in_network": w.net.n_genes, "genes_requested": a.n_genes,
+        "edges": int(w.net.edges_src.shape[0]), "path_length": a.path_length, "permutations": a.n_perms, "top_k": a.top_k,
+        "pairs_per_level": {k: lv[k].n_pairs for k in lv}, "words_per_row_m1": (w.n_patients + 63) // 64,
+        "l2_policy": "inputs larger than L2: path sets + tables per method exceed the 126 MB L2",
+        "seed": a.seed,
+    }
+
+
+def pairs_per_step(w, path_length):
+    names = ["1a", "1b", "2", "3", "4", "5"][: path_length + 1]
+    return sum(w.net.levels[k].n_pairs for k in names) * 2  # methods 1 + 2
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(w, a, target_s, methods=("method1", "method2"), repeats=1):
+    """Times the reference's own JoinExec::join (oracle/_ref) on all host cores over a bounded sample of the level-4
+    join: the first X upstream rows (same W, same permutation count, same value table)."""
+    from geneticscre_b200 import schedule
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    kind = "reference" if po.ref_available() else "port"
+    lv4 = w.net.levels["4"] if a.path_length >= 4 else w.net.levels[str(a.path_length)]
+    last = "4" if a.path_length >= 4 else str(a.path_length)
+    total_pp, total_t, detail = 0.0, 0.0, {}
+    for method in methods:
+        if kind == "reference":
+            ex = po.RefExec(method, w.n_cases, w.n_ctrls, w.n_perms)
+            ex.nthreads = cores
+        else:
+            ex = po.OracleExec(method, w.n_cases, w.n_ctrls, w.n_perms)
+            cores = 1
+        ex.top_k = a.top_k
+        ex.setValueTable(w.value_table)
+        ex.setPermutedMasks(w.perm_masks)
+        t0 = time.time()
+        _, kept = schedule.replay_levels(ex, po.UidRelSet, w, a.path_length - 1 if last == "4" else a.path_length, only=())
+        t_setup = time.time() - t0
+        # calibrate: time a small slice, then size the sample for ~target_s
+        p0_all, p1 = (kept["paths3"], kept["paths2"]) if last == "4" else (None, None)
+        if p0_all is None:
+            raise RuntimeError("cpu baseline needs path_length >= 4")
+        csum = np.cumsum(lv4.count.astype(np.int64))
+
+        def run(x):
+            x = int(min(max(x, 1), lv4.n_uids))
+            uids = po.UidRelSet(4, lv4.src[:x], lv4.trg[:x], lv4.count[:x], lv4.location[:x], lv4.signs[:x])
+            sub = p0_all.select(np.arange(x, dtype=np.int32))
+            t = time.time()
+            ex.join(uids, sub, p1, ex.createPathSet(0))
+            return time.time() - t, int(csum[x - 1])
+
+        x = max(64, lv4.n_uids // 200)
+        t_cal, pairs_cal = run(x)
+        rate = pairs_cal / max(t_cal, 1e-6)
+        want_pairs = rate * target_s
+        x2 = int(np.searchsorted(csum, want_pairs)) + 1
+        best = None
+        for _ in range(repeats):
+            t_run, pairs_run = run(x2)
+            if best is None or pairs_run / t_run > best[1] / best[0]:
+                best = (t_run, pairs_run)
+        total_pp += best[1] * w.n_perms
+        total_t += best[0]
+        detail[method] = {"pairs": best[1], "seconds": round(best[0], 3), "pair_perm_per_s": best[1] * w.n_perms / best[0], "setup_levels_1_3_s": round(t_setup, 2)}
+        del ex
+    value = total_pp / total_t
+    compiler = ""
+    try:
+        compiler = open(os.path.join(ROOT, "oracle", "_ref", "COMPILER.txt")).read().strip()
+    except OSError:
+        pass
+    return {"value": value, "unit": "pair*perm/s", "cores": cores, "kind": kind,
+            "sample": f"level-4 join (paths3 x paths2) over the first upstream rows sized for ~{target_s:.0f} s per method, methods {'+'.join(methods)}, "
+                      f"{w.n_perms} perms, W64={(w.n_patients + 63) // 64}; reference built with {compiler} -O3 -march={po.ref_variant()} -mpopcnt; "
+                      f"nthreads={cores}", "detail": detail}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, _ = make_workload(a)
+    t0 = time.time()
+    vals = []
+    per_step = max(2.0, min(a.cpu_seconds, 60.0 / max(a.steps + a.warmup, 1)))
+    for i in range(a.warmup + a.steps):
+        r = cpu_reference_sample(w, a, per_step / 2)
+        if i >= a.warmup:
+            vals.append(r)
+    value = float(np.mean([v["value"] for v in vals])) if vals else 0.0
+    last = vals[-1] if vals else {"cores": os.cpu_count(), "kind": "reference", "sample": ""}
+    ms = 1e3 * float(np.mean([sum(d["seconds"] for d in v["detail"].values()) for v in vals])) if vals else None
+    line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitsets, u32 counts, f64 scores",
+            "data": "synthetic", "impl": "reference", "config": workload_config(a, w),
+            "cpu_baseline": {"value": value, "unit": "pair*perm/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": value, "unit": "pair*perm/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": round(time.time() - t0, 1)}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def shard_bounds(count, n_shards):
+    """Contiguous upstream-row ranges balanced by pair count (prefix sums of uid.count)."""
+    csum = np.cumsum(count.astype(np.int64))
+    total = int(csum[-1]) if csum.size else 0
+    cuts = [0]
+    for s in range(1, n_shards):
+        cuts.append(int(np.searchsorted(csum, total * s / n_shards)))
+    cuts.append(count.shape[0])
+    return [(cuts[i], max(cuts[i + 1], cuts[i])) for i in range(n_shards)]
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+
+    from geneticscre_b200 import _lib, api, build, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    build.build()
+    lib = _lib.load()
+    kernel = {"auto": _lib.KERNEL_AUTO, "dense": _lib.KERNEL_DENSE, "sparse": _lib.KERNEL_SPARSE}[a.kernel]
+
+    w, gen_s = make_workload(a)
+    lv = w.net.levels
+    n = w.n_patients
+    names = ["1a", "1b", "2", "3", "4", "5"][: a.path_length + 1]
+    last = names[-1]
+    shards = shard_bounds(lv[last].count, world)
+    my_shard = shards[rank]
+    stream = torch.cuda.current_stream()
+
+    def launches():
+        import ctypes
+
+        c = ctypes.c_uint64(0)
+        lib.gcre_kernel_launch_count(ctypes.byref(c))
+        return c.value
+
+    # ---- resident state: one exec per method with table + masks + packed gene rows in HBM ----
+    state = {}
+    for method in ("method1", "method2"):
+        ex = api.JoinExec(method, w.n_cases, w.n_ctrls, w.n_perms, device=local_rank)
+        ex.set_stream(stream.cuda_stream)
+        ex.kernel = kernel
+        ex.top_k = a.top_k
+        ex.setValueTable(w.value_table)
+        ex.setPermutedMasks(w.perm_masks)
+        d1 = ex.createPathSet(w.gene_bits.shape[0])
+        d1.load_bits(w.gene_bits)
+        d2 = ex.createPathSet(w.gene_bits2.shape[0])
+        d2.load_bits(w.gene_bits2)
+        uid = {k: api.UidRelSet(lv[k].path_length, lv[k].src, lv[k].trg, lv[k].count, lv[k].location, lv[k].signs) for k in names}
+        state[method] = dict(ex=ex, d1=d1, d2=d2, uid=uid, perm_t=torch.zeros(ex.iterations, dtype=torch.float32, device="cuda"))
+
+    def schedule_resident(st, results):
+        """Levels 1a,1b,2,3,(4,5) with device-resident inputs; the last level is sharded across ranks."""
+        ex, d1, d2, uid = st["ex"], st["d1"], st["d2"], st["uid"]
+        zero = ex.createPathSet(0)
+        info = {}
+        p1 = ex.createPathSet(lv["1a"].n_pairs)
+        r = ex.join(uid["1a"], ex.createPathSet(lv["1a"].n_uids), d1.select(w.net.data_idx["1a"]), p1); info["1a"] = r.info
+        r = ex.join(uid["1b"], ex.createPathSet(lv["1b"].n_uids), d2.select(w.net.data_idx["1b"]), zero); info["1b"] = r.info; results["1b"] = r
+        prev = p1
+        for k in names[2:]:
+            keep = lv[k].keep and k != last
+            if k in ("2", "3"):
+                operand = d1.select(w.net.data_idx[k])
+            elif k == "4":
+                operand = results["_p2"]
+            else:
+                operand = results["_p3"]
+            res_set = ex.createPathSet(lv[k].n_pairs) if (keep or (k in ("2", "3") and a.path_length > int(k))) else zero
+            if k == last and world > 1:
+                r = ex.join(uid[k], prev, operand, zero, uid_range=my_shard, skip_host_perm=True)
+                lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations)
+                dist.all_reduce(st["perm_t"], op=dist.ReduceOp.MAX)  # ONE collective per join: NCCL allreduce(max)
+                gathered = [None] * world
+                dist.all_gather_object(gathered, [(s.score, s.src, s.trg, s.cases, s.ctrls) for s in r.scores])
+                r.scores = api.merge_topk([[api.Score(*t) for t in g] for g in gathered], a.top_k)
+                r.permuted_scores = st["perm_t"][: w.n_perms].double().cpu().numpy()
+            else:
+                r = ex.join(uid[k], prev, operand, res_set)
+            info[k] = r.info
+            results[k] = r
+            if k == "2":
+                results["_p2"] = res_set
+            if k == "3":
+                results["_p3"] = res_set
+            if k in ("2", "3"):
+                prev = res_set
+        return info
+
+    def step_resident():
+        out = {}
+        for method in ("method1", "method2"):
+            res = {}
+            out[method] = (schedule_resident(state[method], res), res)
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up + timed region (CUDA events on the stream the engine launches on) ----
+    for _ in range(a.warmup):
+        step_resident()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    last_out = None
+    for _ in range(a.steps):
+        last_out = step_resident()
+    ev1.record(stream)
+    sync_all()
+    ms_total = ev0.elapsed_time(ev1)
+    n_launch = launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = float(t_ms.item()) / a.steps
+    pp_step = pairs_per_step(w, a.path_length) * w.n_perms
+    value = pp_step / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel: the last-level join of each method, timed live by CUDA events inside join ----
+    roof = None
+    if last_out is not None:
+        W64 = (n + 63) // 64
+        ker_ms, alg_bytes, word_ops, kname = 0.0, 0.0, 0.0, None
+        for method, m in (("method1", 1), ("method2", 2)):
+            inf = last_out[method][0][last]
+            ker_ms += inf["kernel_ms"]
+            pairs = inf["pairs"]
+            alg_bytes += pairs * 2 * W64 * m * 8 + W64 * w.n_perms * 8 + 4 * w.n_perms
+            word_ops += pairs * w.n_perms * W64 * m
+            kname = {1: "dense", 2: "sparse"}.get(inf["kernel"], "?")
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        int_peak = 148 * 16 * sm_mhz * 1e6 / 2.0  # 16 POPC32/clk/SM nominal, 2 per 64-bit word-op
+        ach = alg_bytes / (ker_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "kernel": f"join_{kname}_kernel, level-{last} joins of methods 1+2 (this rank's shard)", "kernel_ms_per_step": ker_ms,
+                "kernel_share_of_step": ker_ms / ms_step,
+                "int_word_ops_per_s": word_ops / (ker_ms * 1e-3), "int_peak_word_ops_per_s_nominal": int_peak,
+                "int_frac_nominal": word_ops / (ker_ms * 1e-3) / int_peak,
+                "note": "integer-bound kernel: the HBM fraction is reported per contract; the binding roof is the INT/POPC pipe (SURVEY App. E)"}
+
+    # ---- end-to-end through the reference-facing calls with HOST buffers (R-facing int matrices), N GPUs ----
+    e2e = None
+    if not a.no_e2e:
+        data1_i = torch.from_numpy(synth.unpack_bits(w.gene_bits, n)).pin_memory().numpy()
+        data2_i = torch.from_numpy(synth.unpack_bits(w.gene_bits2, n)).pin_memory().numpy()
+        bits = np.unpackbits(w.perm_masks.view(np.uint8), axis=1, bitorder="little")[:, :n].astype(bool)
+        is_case = np.zeros(n, dtype=bool)
+        is_case[: w.n_cases] = True
+        perm_i = torch.from_numpy((bits == is_case[None, :]).astype(np.int32)).pin_memory().numpy()
+        table = torch.from_numpy(np.ascontiguousarray(w.value_table)).pin_memory().numpy()
+        h2d = (data1_i.nbytes + data2_i.nbytes + perm_i.nbytes + table.nbytes) * 2  # per method
+        d2h_holder = [0]
+
+        def step_e2e():
+            d2h = 0
+            for method in ("method1", "method2"):
+                ex = api.JoinExec(method, w.n_cases, w.n_ctrls, w.n_perms, device=local_rank)
+                ex.kernel = kernel
+                ex.top_k = a.top_k
+                ex.setValueTable(table)
+                ex.setPermutedCases(perm_i)
+                d1 = ex.createPathSet(data1_i.shape[0]); d1.load(data1_i)
+                d2 = ex.createPathSet(data2_i.shape[0]); d2.load(data2_i)
+                st = dict(ex=ex, d1=d1, d2=d2, uid=state[method]["uid"], perm_t=state[method]["perm_t"])
+                res = {}
+                schedule_resident(st, res)
+                for k, r in res.items():
+                    if not k.startswith("_"):
+                        d2h += r.permuted_scores.nbytes // 2 + len(r.scores) * 24
+                del res, st, d1, d2
+                ex.close()
+            d2h_holder[0] = d2h
+
+        step_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(a.steps, 3))
+        for _ in range(e2e_steps):
+            step_e2e()
+        sync_all()
+        dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": pp_step / float(dt.item()), "unit": "pair*perm/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_holder[0]),
+               "ms_per_step": float(dt.item()) * 1e3, "steps": e2e_steps,
+               "note": "host IntegerMatrix data + CaseORControl int matrix + f64 value table uploaded every step (pinned), per method"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            cpu = cpu_reference_sample(w, a, a.cpu_seconds)
+        except Exception as e:  # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": "pair*perm/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}
+
+    if rank == 0:
+        line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u64 bitsets, u32 counts, f64 scores", "data": "synthetic", "config": workload_config(a, w), "clocks": clocks,
+                "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu,
+                "pair_perm_per_step": pp_step, "workload_gen_s": round(gen_s, 1)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,818 @@
+// C ABI of the B200 join engine (include/gcre_b200.h): host-side orchestration of the CUDA kernels.
+// Stands in for JoinExec / PathSet of the reference (src/join_base.cpp, src/gcre_paths.h); no CPU compute path.
+#include "../../include/gcre_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "setup_kernels.cuh"
+#include "join_dense.cuh"
+#include "join_sparse.cuh"
+
+using namespace gcre;
+
+// ------------------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(e__ == cudaErrorMemoryAllocation ? GCRE_ERR_NOMEM : GCRE_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                          \
+  } while (0)
+
+#define CKS(call)            \
+  do {                       \
+    int s__ = (call);        \
+    if (s__ != GCRE_OK) return s__; \
+  } while (0)
+
+static std::atomic<unsigned long long> g_launches{0};
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+static inline unsigned grid_for(long long items, int block) { return (unsigned)((items + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------------------------------
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return GCRE_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&p, want));
+    cap = want;
+    return GCRE_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct gcre_exec {
+  int M = 1, n_cases = 0, n_ctrls = 0, n = 0, W64 = 0, Wp = 0, iters = 0, Ip = 0, Iw = 0, device = 0, sm_count = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // permutation masks
+  uint64_t* d_masks = nullptr;  // canonical perm-major [iters][W64]
+  uint64_t* d_pm = nullptr;     // word-major [Wp][Ip]
+  uint32_t* d_pt = nullptr;     // patient-major [n][Iw], built on first use by a sparse kernel
+  bool pt_valid = false;
+  // value table
+  double* d_vt = nullptr;
+  int vt_rows = 0, vt_cols = 0;
+  double* d_diagD = nullptr;
+  float* d_diagF = nullptr;
+  double* d_diagDM = nullptr;
+  long long diag_cap = -1;
+  // outputs / scratch
+  int* d_perm_max = nullptr;
+  unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total
+  DevBuf cand, uid_count, uid_loc, uid_prefix, uid_res, signs, scratch;
+  unsigned* h_scalars = nullptr;  // pinned
+};
+
+struct gcre_pathset {
+  const gcre_exec* ex = nullptr;
+  uint32_t size = 0;
+  uint64_t* d_rows = nullptr;
+  long long max_half_pop = 0;  // max carriers in any half-row; -1 = unknown (recomputed on demand)
+};
+
+static int use_device(const gcre_exec* ex) {
+  CK(cudaSetDevice(ex->device));
+  return GCRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// misc
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" const char* gcre_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* gcre_version(void) { return "gcre-b200 0.1 (sm_100a)"; }
+
+extern "C" int gcre_kernel_launch_count(uint64_t* count) {
+  if (!count) return fail(GCRE_ERR_ARG, "null argument");
+  *count = g_launches.load();
+  return GCRE_OK;
+}
+
+extern "C" int gcre_device_count(int* count) {
+  if (!count) return fail(GCRE_ERR_ARG, "null argument");
+  CK(cudaGetDeviceCount(count));
+  return GCRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// exec
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int iters, int device, gcre_exec** out) {
+  if (!out) return fail(GCRE_ERR_ARG, "null argument");
+  *out = nullptr;
+  // src/join_base.cpp:47: check_true(num_cases > 0 && num_ctrls > 0 && iters >= 0)
+  if (!(num_cases > 0 && num_ctrls > 0 && iters >= 0)) return fail(GCRE_ERR_ASSERT, "assertion");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) return fail(GCRE_ERR_CUDA, "no CUDA device (this engine has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(GCRE_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  gcre_exec* ex = new (std::nothrow) gcre_exec();
+  if (!ex) return fail(GCRE_ERR_NOMEM, "host allocation failed");
+  ex->M = (method == 1) ? 1 : 2;  // JoinExec::to_method: anything but "method1" is method 2 (src/gcre.h:125-133)
+  ex->n_cases = num_cases;
+  ex->n_ctrls = num_ctrls;
+  ex->n = num_cases + num_ctrls;
+  ex->W64 = (ex->n + 63) / 64;
+  ex->Wp = (ex->W64 + 1) & ~1;
+  ex->iters = iters;
+  ex->Ip = ((std::max(iters, 1) + dense::TI - 1) / dense::TI) * dense::TI;
+  ex->Iw = ex->Ip / 32;
+  ex->device = device;
+  int rc = [&]() -> int {
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceGetAttribute(&ex->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&ex->own_stream, cudaStreamNonBlocking));
+    ex->stream = ex->own_stream;
+    CK(cudaEventCreate(&ex->ev0));
+    CK(cudaEventCreate(&ex->ev1));
+    CK(cudaMalloc(&ex->d_masks, std::max<size_t>((size_t)iters * ex->W64, 1) * 8));
+    CK(cudaMalloc(&ex->d_pm, (size_t)ex->Wp * ex->Ip * 8));
+    CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)iters * ex->W64, 1) * 8, ex->stream));
+    CK(cudaMemsetAsync(ex->d_pm, 0, (size_t)ex->Wp * ex->Ip * 8, ex->stream));
+    CK(cudaMalloc(&ex->d_perm_max, (size_t)ex->Ip * 4));
+    CK(cudaMemsetAsync(ex->d_perm_max, 0, (size_t)ex->Ip * 4, ex->stream));
+    CK(cudaMalloc(&ex->d_scalars, 16 * sizeof(unsigned)));
+    CK(cudaMemsetAsync(ex->d_scalars, 0, 16 * sizeof(unsigned), ex->stream));
+    CK(cudaMallocHost(&ex->h_scalars, 16 * sizeof(unsigned)));
+    CK(cudaStreamSynchronize(ex->stream));
+    return GCRE_OK;
+  }();
+  if (rc != GCRE_OK) {
+    gcre_exec_destroy(ex);
+    return rc;
+  }
+  *out = ex;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_destroy(gcre_exec* ex) {
+  if (!ex) return GCRE_OK;
+  cudaSetDevice(ex->device);
+  if (ex->own_stream) cudaStreamSynchronize(ex->own_stream);
+  cudaFree(ex->d_masks);
+  cudaFree(ex->d_pm);
+  cudaFree(ex->d_pt);
+  cudaFree(ex->d_vt);
+  cudaFree(ex->d_diagD);
+  cudaFree(ex->d_diagF);
+  cudaFree(ex->d_diagDM);
+  cudaFree(ex->d_perm_max);
+  cudaFree(ex->d_scalars);
+  if (ex->h_scalars) cudaFreeHost(ex->h_scalars);
+  ex->cand.release();
+  ex->uid_count.release();
+  ex->uid_loc.release();
+  ex->uid_prefix.release();
+  ex->uid_res.release();
+  ex->signs.release();
+  ex->scratch.release();
+  if (ex->ev0) cudaEventDestroy(ex->ev0);
+  if (ex->ev1) cudaEventDestroy(ex->ev1);
+  if (ex->own_stream) cudaStreamDestroy(ex->own_stream);
+  delete ex;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_get_info(const gcre_exec* ex, gcre_exec_info* out) {
+  if (!ex || !out) return fail(GCRE_ERR_ARG, "null argument");
+  out->method = ex->M;
+  out->num_cases = ex->n_cases;
+  out->num_ctrls = ex->n_ctrls;
+  out->width_ul = ex->Wp;
+  out->iterations = ex->Ip;
+  out->iters_requested = ex->iters;
+  out->device = ex->device;
+  out->sm_count = ex->sm_count;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_set_stream(gcre_exec* ex, void* cuda_stream) {
+  if (!ex) return fail(GCRE_ERR_ARG, "null argument");
+  CKS(use_device(ex));
+  CK(cudaStreamSynchronize(ex->stream));
+  ex->stream = cuda_stream ? (cudaStream_t)cuda_stream : ex->own_stream;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_set_value_table(gcre_exec* ex, const double* table, int rows, int cols) {
+  if (!ex || (!table && rows > 0 && cols > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  if (rows < 0 || cols < 0) return fail(GCRE_ERR_ARG, "negative table size");
+  CKS(use_device(ex));
+  CK(cudaStreamSynchronize(ex->stream));
+  cudaFree(ex->d_vt);
+  ex->d_vt = nullptr;
+  // the reference keeps at most the top-left (n+1)x(n+1) block (src/join_base.cpp:74-78); larger inputs are legal
+  ex->vt_rows = rows;
+  ex->vt_cols = cols;
+  const size_t bytes = std::max<size_t>((size_t)rows * cols, 1) * 8;
+  CK(cudaMalloc(&ex->d_vt, bytes));
+  if ((size_t)rows * cols > 0) CK(cudaMemcpyAsync(ex->d_vt, table, (size_t)rows * cols * 8, cudaMemcpyHostToDevice, ex->stream));
+  CK(cudaStreamSynchronize(ex->stream));
+  ex->diag_cap = -1;  // anti-diagonal tables are rebuilt on the next join
+  return GCRE_OK;
+}
+
+static int rebuild_mask_layouts(gcre_exec* ex) {
+  CK(cudaMemsetAsync(ex->d_pm, 0, (size_t)ex->Wp * ex->Ip * 8, ex->stream));
+  if (ex->iters > 0) {
+    dim3 blk(32, 8), grd((ex->iters + 31) / 32, (ex->W64 + 31) / 32);
+    masks_to_word_major_kernel<<<grd, blk, 0, ex->stream>>>(ex->d_masks, ex->iters, ex->W64, ex->d_pm, ex->Wp, ex->Ip);
+    CK(cudaGetLastError());
+      LAUNCHED();
+  }
+  ex->pt_valid = false;
+  return GCRE_OK;
+}
+
+static int ensure_patient_major(gcre_exec* ex) {
+  if (ex->pt_valid) return GCRE_OK;
+  if (!ex->d_pt) CK(cudaMalloc(&ex->d_pt, std::max<size_t>((size_t)ex->n * ex->Iw, 1) * 4));
+  const long long warps = (long long)ex->Iw * ((ex->n + 31) / 32);
+  masks_to_patient_major_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>(ex->d_masks, ex->iters, ex->W64, ex->n, ex->d_pt, ex->Iw);
+  CK(cudaGetLastError());
+      LAUNCHED();
+  ex->pt_valid = true;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_set_permuted_cases_i32(gcre_exec* ex, const int32_t* perm, int rows, int cols) {
+  if (!ex || (!perm && rows > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  if (rows < 0 || cols < 0) return fail(GCRE_ERR_ARG, "negative size");
+  CKS(use_device(ex));
+  const int have = std::min(rows, ex->iters);
+  // src/join_base.cpp:101: check_equal(num_cases + num_ctrls, data[r].size())
+  if (have > 0 && cols != ex->n) return fail(GCRE_ERR_ASSERT, "assertion");
+  // src/join_base.cpp:116-123 would divide by zero with no rows and iters > 0: reject instead
+  if (ex->iters > 0 && rows == 0) return fail(GCRE_ERR_ASSERT, "assertion");
+  CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)ex->iters * ex->W64, 1) * 8, ex->stream));
+  // upload and pack in row blocks of <= 256 MB
+  const int rows_per_blk = (int)std::max<size_t>(1, ((size_t)256 << 20) / ((size_t)std::max(cols, 1) * 4));
+  CKS(ex->scratch.ensure((size_t)std::min(rows_per_blk, std::max(have, 1)) * std::max(cols, 1) * 4));
+  for (int r0 = 0; r0 < have; r0 += rows_per_blk) {
+    const int nr = std::min(rows_per_blk, have - r0);
+    CK(cudaMemcpyAsync(ex->scratch.p, perm + (size_t)r0 * cols, (size_t)nr * cols * 4, cudaMemcpyHostToDevice, ex->stream));
+    const long long warps = (long long)nr * ex->W64;
+    pack_perm_i32_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>((const int32_t*)ex->scratch.p, nr, cols, ex->n_cases, ex->W64,
+                                                                           ex->d_masks, r0);
+    CK(cudaGetLastError());
+      LAUNCHED();
+    CK(cudaStreamSynchronize(ex->stream));  // scratch is reused by the next block
+  }
+  if (have < ex->iters) {
+    cycle_perm_rows_kernel<<<grid_for((long long)(ex->iters - have) * ex->W64, 256), 256, 0, ex->stream>>>(ex->d_masks, have, ex->iters, ex->W64);
+    CK(cudaGetLastError());
+      LAUNCHED();
+  }
+  CKS(rebuild_mask_layouts(ex));
+  CK(cudaStreamSynchronize(ex->stream));
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_set_permuted_masks_u64(gcre_exec* ex, const uint64_t* masks, int n_perms) {
+  if (!ex || (!masks && n_perms > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  CKS(use_device(ex));
+  if (ex->iters > 0 && n_perms <= 0) return fail(GCRE_ERR_ASSERT, "assertion");
+  const int have = std::min(n_perms, ex->iters);
+  CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)ex->iters * ex->W64, 1) * 8, ex->stream));
+  if (have > 0) CK(cudaMemcpyAsync(ex->d_masks, masks, (size_t)have * ex->W64 * 8, cudaMemcpyHostToDevice, ex->stream));
+  if (have < ex->iters) {
+    cycle_perm_rows_kernel<<<grid_for((long long)(ex->iters - have) * ex->W64, 256), 256, 0, ex->stream>>>(ex->d_masks, have, ex->iters, ex->W64);
+    CK(cudaGetLastError());
+      LAUNCHED();
+  }
+  CKS(rebuild_mask_layouts(ex));
+  CK(cudaStreamSynchronize(ex->stream));
+  return GCRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// path sets
+// ------------------------------------------------------------------------------------------------------------------
+static inline size_t row_words(const gcre_exec* ex) { return (size_t)ex->Wp * ex->M; }
+
+extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_pathset** out) {
+  if (!ex || !out) return fail(GCRE_ERR_ARG, "null argument");
+  *out = nullptr;
+  CKS(use_device(ex));
+  gcre_pathset* ps = new (std::nothrow) gcre_pathset();
+  if (!ps) return fail(GCRE_ERR_NOMEM, "host allocation failed");
+  ps->ex = ex;
+  ps->size = size;
+  const size_t bytes = (size_t)size * row_words(ex) * 8;
+  if (bytes) {
+    cudaError_t e = cudaMalloc(&ps->d_rows, bytes);
+    if (e != cudaSuccess) {
+      delete ps;
+      return fail(GCRE_ERR_NOMEM, "cudaMalloc of %zu bytes for a path set failed: %s", bytes, cudaGetErrorString(e));
+    }
+    e = cudaMemsetAsync(ps->d_rows, 0, bytes, ex->stream);
+    if (e != cudaSuccess) {
+      cudaFree(ps->d_rows);
+      delete ps;
+      return fail(GCRE_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = ps;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_pathset_destroy(gcre_pathset* ps) {
+  if (!ps) return GCRE_OK;
+  cudaSetDevice(ps->ex->device);
+  cudaStreamSynchronize(ps->ex->stream);
+  cudaFree(ps->d_rows);
+  delete ps;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_pathset_size(const gcre_pathset* ps, uint32_t* size) {
+  if (!ps || !size) return fail(GCRE_ERR_ARG, "null argument");
+  *size = ps->size;
+  return GCRE_OK;
+}
+
+static int pathset_max_half_pop(gcre_pathset* ps, long long* out) {
+  gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
+  if (ps->max_half_pop < 0) {
+    CK(cudaMemsetAsync(ex->d_scalars + 1, 0, sizeof(unsigned), ex->stream));
+    if (ps->size) {
+      const long long warps = (long long)ps->size * ex->M;
+      if (ex->M == 1)
+        row_maxpop_kernel<1><<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, ps->size, ex->Wp, ex->d_scalars + 1);
+      else
+        row_maxpop_kernel<2><<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, ps->size, ex->Wp, ex->d_scalars + 1);
+      CK(cudaGetLastError());
+      LAUNCHED();
+    }
+    CK(cudaMemcpyAsync(ex->h_scalars + 1, ex->d_scalars + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaStreamSynchronize(ex->stream));
+    ps->max_half_pop = ex->h_scalars[1];
+  }
+  *out = ps->max_half_pop;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint32_t rows, int cols) {
+  if (!ps || (!data && rows > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
+  CKS(use_device(ex));
+  // src/gcre_paths.h:60: check_true(size == data.size())
+  if (rows != ps->size) return fail(GCRE_ERR_ASSERT, "assertion");
+  // src/gcre_paths.h:63: check_index(data[r].size(), width_ul * 64); our rows hold W64*64 patients, and a column count
+  // equal to n is always accepted (the reference throws when n is a multiple of its SIMD width: SURVEY App. D1)
+  if (rows > 0 && (cols < 0 || cols > ex->W64 * 64)) return fail(GCRE_ERR_RANGE, "assertion");
+  if (rows == 0) return GCRE_OK;
+  CK(cudaMemsetAsync(ps->d_rows, 0, (size_t)ps->size * row_words(ex) * 8, ex->stream));
+  const uint32_t rows_per_blk = (uint32_t)std::max<size_t>(1, ((size_t)256 << 20) / ((size_t)std::max(cols, 1) * 4));
+  CKS(ex->scratch.ensure((size_t)std::min(rows_per_blk, rows) * std::max(cols, 1) * 4));
+  for (uint32_t r0 = 0; r0 < rows; r0 += rows_per_blk) {
+    const uint32_t nr = std::min(rows_per_blk, rows - r0);
+    CK(cudaMemcpyAsync(ex->scratch.p, data + (size_t)r0 * cols, (size_t)nr * cols * 4, cudaMemcpyHostToDevice, ex->stream));
+    const long long warps = (long long)nr * ex->W64;
+    pack_rows_i32_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>((const int32_t*)ex->scratch.p, nr, cols,
+                                                                           ps->d_rows + (size_t)r0 * row_words(ex), (int)row_words(ex), ex->W64);
+    CK(cudaGetLastError());
+      LAUNCHED();
+    CK(cudaStreamSynchronize(ex->stream));
+  }
+  ps->max_half_pop = -1;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_pathset_load_bits(gcre_pathset* ps, const uint64_t* bits, uint32_t rows, int words_per_row) {
+  if (!ps || (!bits && rows > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
+  CKS(use_device(ex));
+  if (rows != ps->size) return fail(GCRE_ERR_ASSERT, "assertion");
+  if (rows > 0 && (words_per_row < 0 || words_per_row > ex->W64)) return fail(GCRE_ERR_RANGE, "assertion");
+  if (rows == 0) return GCRE_OK;
+  CK(cudaMemsetAsync(ps->d_rows, 0, (size_t)ps->size * row_words(ex) * 8, ex->stream));
+  const size_t bytes = (size_t)rows * words_per_row * 8;
+  if (bytes) {
+    CKS(ex->scratch.ensure(bytes));
+    CK(cudaMemcpyAsync(ex->scratch.p, bits, bytes, cudaMemcpyHostToDevice, ex->stream));
+    place_rows_kernel<<<grid_for((long long)rows * words_per_row, 256), 256, 0, ex->stream>>>((const uint64_t*)ex->scratch.p, rows, words_per_row,
+                                                                                             words_per_row, ps->d_rows, (int)row_words(ex));
+    CK(cudaGetLastError());
+      LAUNCHED();
+    CK(cudaStreamSynchronize(ex->stream));
+  }
+  ps->max_half_pop = -1;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_pathset_select(const gcre_pathset* ps, const int32_t* indices, uint32_t n, gcre_pathset** out) {
+  if (!ps || !out || (!indices && n > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  *out = nullptr;
+  gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
+  CKS(use_device(ex));
+  // src/gcre_paths.h:85: check_index(indices[k], size)
+  for (uint32_t k = 0; k < n; k++)
+    if (indices[k] < 0 || (uint32_t)indices[k] >= ps->size) return fail(GCRE_ERR_RANGE, "assertion");
+  gcre_pathset* res = nullptr;
+  CKS(gcre_pathset_create(ex, n, &res));
+  if (n) {
+    int rc = [&]() -> int {
+      CKS(ex->scratch.ensure((size_t)n * 4));
+      CK(cudaMemcpyAsync(ex->scratch.p, indices, (size_t)n * 4, cudaMemcpyHostToDevice, ex->stream));
+      const int row_vec = (int)(row_words(ex) / 2);
+      select_rows_kernel<<<grid_for((long long)n * row_vec, 256), 256, 0, ex->stream>>>((const ulonglong2*)ps->d_rows, (const int32_t*)ex->scratch.p, n,
+                                                                                       row_vec, (ulonglong2*)res->d_rows);
+      CK(cudaGetLastError());
+      LAUNCHED();
+      CK(cudaStreamSynchronize(ex->stream));
+      return GCRE_OK;
+    }();
+    if (rc != GCRE_OK) {
+      gcre_pathset_destroy(res);
+      return rc;
+    }
+  }
+  res->max_half_pop = ps->max_half_pop;  // an upper bound is all that is needed
+  *out = res;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_pathset_set_row(gcre_pathset* ps, uint32_t idx, const uint64_t* words) {
+  if (!ps || !words) return fail(GCRE_ERR_ARG, "null argument");
+  gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
+  CKS(use_device(ex));
+  if (idx >= ps->size) return fail(GCRE_ERR_RANGE, "assertion");  // src/gcre_paths.h:50
+  for (int h = 0; h < ex->M; h++)
+    CK(cudaMemcpyAsync(ps->d_rows + (size_t)idx * row_words(ex) + (size_t)h * ex->Wp, words + (size_t)h * ex->W64, (size_t)ex->W64 * 8,
+                       cudaMemcpyHostToDevice, ex->stream));
+  CK(cudaStreamSynchronize(ex->stream));
+  ps->max_half_pop = -1;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_pathset_get_row(const gcre_pathset* ps, uint32_t idx, uint64_t* words) {
+  if (!ps || !words) return fail(GCRE_ERR_ARG, "null argument");
+  const gcre_exec* ex = ps->ex;
+  CKS(use_device(ex));
+  if (idx >= ps->size) return fail(GCRE_ERR_RANGE, "assertion");  // src/gcre_paths.h:45
+  for (int h = 0; h < ex->M; h++)
+    CK(cudaMemcpyAsync(words + (size_t)h * ex->W64, ps->d_rows + (size_t)idx * row_words(ex) + (size_t)h * ex->Wp, (size_t)ex->W64 * 8,
+                       cudaMemcpyDeviceToHost, ex->stream));
+  CK(cudaStreamSynchronize(ex->stream));
+  return GCRE_OK;
+}
+
+extern "C" int gcre_pathset_download(const gcre_pathset* ps, uint64_t* out) {
+  if (!ps || (!out && ps->size)) return fail(GCRE_ERR_ARG, "null argument");
+  gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
+  CKS(use_device(ex));
+  if (!ps->size) return GCRE_OK;
+  const size_t words = (size_t)ps->size * ex->W64 * ex->M;
+  CKS(ex->scratch.ensure(words * 8));
+  if (ex->M == 1)
+    unpad_rows_kernel<1><<<grid_for((long long)words, 256), 256, 0, ex->stream>>>(ps->d_rows, ps->size, ex->Wp, ex->W64, (uint64_t*)ex->scratch.p);
+  else
+    unpad_rows_kernel<2><<<grid_for((long long)words, 256), 256, 0, ex->stream>>>(ps->d_rows, ps->size, ex->Wp, ex->W64, (uint64_t*)ex->scratch.p);
+  CK(cudaGetLastError());
+      LAUNCHED();
+  CK(cudaMemcpyAsync(out, ex->scratch.p, words * 8, cudaMemcpyDeviceToHost, ex->stream));
+  CK(cudaStreamSynchronize(ex->stream));
+  return GCRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// value-table re-layout
+// ------------------------------------------------------------------------------------------------------------------
+static int ensure_diag(gcre_exec* ex, long long t_needed) {
+  if (t_needed <= ex->diag_cap) return GCRE_OK;
+  if (!ex->d_vt) {
+    // no table set: the reference's value_table would be empty and indexing it is undefined; treat as all -1.0
+    CK(cudaMalloc(&ex->d_vt, 8));
+    ex->vt_rows = ex->vt_cols = 0;
+  }
+  long long cap = std::min<long long>(ex->n, std::max<long long>(t_needed + t_needed / 4 + 64, 1024));
+  cap = std::max(cap, t_needed);
+  CK(cudaStreamSynchronize(ex->stream));
+  cudaFree(ex->d_diagD);
+  cudaFree(ex->d_diagF);
+  cudaFree(ex->d_diagDM);
+  ex->d_diagD = nullptr;
+  ex->d_diagF = nullptr;
+  ex->d_diagDM = nullptr;
+  ex->diag_cap = -1;
+  const size_t entries = (size_t)(cap + 1) * (size_t)(cap + 2) / 2;
+  CK(cudaMalloc(&ex->d_diagD, entries * 8));
+  if (ex->M == 1) CK(cudaMalloc(&ex->d_diagF, entries * 4));
+  else CK(cudaMalloc(&ex->d_diagDM, entries * 8));
+  build_diag_kernel<<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_vt, ex->vt_rows, ex->vt_cols, (unsigned)cap, ex->d_diagD, ex->d_diagF, ex->d_diagDM);
+  CK(cudaGetLastError());
+      LAUNCHED();
+  ex->diag_cap = cap;
+  return GCRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// top-K bookkeeping (host): K largest scores, ties broken by smaller (src, trg)
+// ------------------------------------------------------------------------------------------------------------------
+static inline bool better(const gcre_score& a, const gcre_score& b) {
+  if (a.score != b.score) return a.score > b.score;
+  if (a.src != b.src) return (uint32_t)a.src < (uint32_t)b.src;
+  return (uint32_t)a.trg < (uint32_t)b.trg;
+}
+
+static void trim_topk(std::vector<gcre_score>& held, int top_k) {
+  if ((int)held.size() > top_k) {
+    std::nth_element(held.begin(), held.begin() + top_k, held.end(), better);
+    held.resize(top_k);
+  }
+}
+
+// src/join_base.cpp:138-154: ascending order, leading -inf sentinel when fewer than top_k real entries
+static int emit_topk(std::vector<gcre_score>& held, int top_k, gcre_score* out_scores, int* n_scores) {
+  trim_topk(held, top_k);
+  std::sort(held.begin(), held.end(), better);
+  int n = 0;
+  if ((int)held.size() < top_k) {
+    gcre_score s;
+    s.score = -std::numeric_limits<double>::infinity();
+    s.src = -1;
+    s.trg = -1;
+    s.cases = 0;
+    s.ctrls = 0;
+    out_scores[n++] = s;
+  }
+  for (int k = (int)held.size() - 1; k >= 0; k--) out_scores[n++] = held[k];
+  *n_scores = n;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_merge_topk(const gcre_score* lists, const int* list_sizes, int n_lists, int top_k, gcre_score* out_scores, int* n_scores) {
+  if (!lists || !list_sizes || !out_scores || !n_scores) return fail(GCRE_ERR_ARG, "null argument");
+  if (top_k < 1) top_k = 1;
+  std::vector<gcre_score> held;
+  size_t off = 0;
+  for (int l = 0; l < n_lists; l++) {
+    for (int k = 0; k < list_sizes[l]; k++)
+      if (lists[off + k].src >= 0) held.push_back(lists[off + k]);
+    off += list_sizes[l];
+  }
+  return emit_topk(held, top_k, out_scores, n_scores);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// join
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(gcre_exec* ex, DevBuf& buf, const std::vector<T>& v) {
+  CKS(buf.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) CK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ex->stream));
+  return GCRE_OK;
+}
+
+static int launch_join(gcre_exec* ex, const JoinParams& jp, bool keep, int kernel, int* launches) {
+  const unsigned long long n_pairs = jp.pair_end - jp.pair_begin;
+  if (n_pairs == 0) return GCRE_OK;
+  if (kernel == GCRE_KERNEL_SPARSE) return launch_join_sparse(ex->stream, jp, ex->M, keep, ex->sm_count, launches);
+  const unsigned long long tiles = (n_pairs + dense::TP - 1) / dense::TP;
+  const unsigned long long blocks = tiles * jp.n_perm_tiles;
+  if (blocks > 0x7fffffffull) return fail(GCRE_ERR_ARG, "join chunk too large");
+  const unsigned g = (unsigned)blocks;
+  if (ex->M == 1) {
+    if (keep) join_dense_kernel<1, true><<<g, dense::THREADS, 0, ex->stream>>>(jp);
+    else join_dense_kernel<1, false><<<g, dense::THREADS, 0, ex->stream>>>(jp);
+  } else {
+    if (keep) join_dense_kernel<2, true><<<g, dense::THREADS, 0, ex->stream>>>(jp);
+    else join_dense_kernel<2, false><<<g, dense::THREADS, 0, ex->stream>>>(jp);
+  }
+  CK(cudaGetLastError());
+      LAUNCHED();
+  (*launches)++;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uids, uint32_t n_uids, const int32_t* signs, uint32_t n_signs,
+                         const gcre_pathset* paths0, const gcre_pathset* paths1, gcre_pathset* paths_res, int top_k, gcre_score* out_scores,
+                         int* n_scores, double* out_perm, gcre_join_opts* opts) {
+  if (!ex || !paths0 || !paths1 || !out_scores || !n_scores || (!uids && n_uids) || (!signs && n_signs))
+    return fail(GCRE_ERR_ARG, "null argument");
+  if (!out_perm && ex->iters > 0 && !(opts && opts->skip_host_perm)) return fail(GCRE_ERR_ARG, "null argument");
+  if (paths0->ex != ex || paths1->ex != ex || (paths_res && paths_res->ex != ex)) return fail(GCRE_ERR_ARG, "path set belongs to another exec");
+  CKS(use_device(ex));
+  if (top_k < 1) top_k = 1;
+  const bool keep = paths_res && paths_res->size != 0;
+
+  // ---- pre-checks, src/join_base.cpp:196-200 ----
+  if (n_uids != paths0->size) return fail(GCRE_ERR_ASSERT, "assertion");
+  std::vector<int32_t> h_count(n_uids);
+  std::vector<uint32_t> h_loc(n_uids);
+  std::vector<unsigned long long> h_prefix((size_t)n_uids + 1), h_res(n_uids);
+  unsigned long long total = 0;
+  unsigned long long max_loc_end = 0;
+  for (uint32_t u = 0; u < n_uids; u++) {
+    const int32_t c = uids[u].count > 0 ? uids[u].count : 0;
+    h_count[u] = c;
+    h_loc[u] = uids[u].location;
+    h_prefix[u] = total;
+    h_res[u] = uids[u].path_idx;
+    if (c > 0) {
+      const unsigned long long last = (unsigned long long)uids[u].location + c - 1;
+      if (last >= paths1->size) return fail(GCRE_ERR_RANGE, "assertion");
+      max_loc_end = std::max(max_loc_end, last + 1);
+      if (keep && uids[u].path_idx + c > paths_res->size) return fail(GCRE_ERR_RANGE, "assertion");
+    }
+    total += c;
+  }
+  h_prefix[n_uids] = total;
+  if (paths_res && !(paths_res->size == 0 || paths_res->size == total)) return fail(GCRE_ERR_ASSERT, "assertion");
+  if (ex->M == 2 && total > 0) {
+    // need_flip indexes signs by upstream row and/or partner row (src/gcre.h:71-81); the reference reads unchecked
+    const unsigned long long need = path_length > 3 ? n_uids : (path_length < 3 ? max_loc_end : std::max<unsigned long long>(n_uids, max_loc_end));
+    if (n_signs < need) return fail(GCRE_ERR_RANGE, "assertion");
+  }
+
+  uint32_t ub = 0, ue = n_uids;
+  if (opts && opts->uid_end != 0) {
+    ub = std::min(opts->uid_begin, n_uids);
+    ue = std::min(std::max(opts->uid_end, ub), n_uids);
+  }
+  const unsigned long long pair_lo = h_prefix[ub], pair_hi = h_prefix[ue];
+
+  // ---- value-table coverage: a joined half-row has at most maxpop0 + maxpop1 carriers ----
+  long long mp0 = 0, mp1 = 0;
+  CKS(pathset_max_half_pop(const_cast<gcre_pathset*>(paths0), &mp0));
+  CKS(pathset_max_half_pop(const_cast<gcre_pathset*>(paths1), &mp1));
+  const long long t_needed = std::min<long long>(ex->n, mp0 + mp1);
+  CKS(ensure_diag(ex, t_needed));
+
+  // ---- kernel choice ----
+  int kernel = opts ? opts->kernel : GCRE_KERNEL_AUTO;
+  if (kernel != GCRE_KERNEL_DENSE && kernel != GCRE_KERNEL_SPARSE) kernel = sparse_supported(ex->n, t_needed) ? GCRE_KERNEL_SPARSE : GCRE_KERNEL_DENSE;
+  if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed)) kernel = GCRE_KERNEL_DENSE;
+  if (kernel == GCRE_KERNEL_SPARSE) CKS(ensure_patient_major(ex));
+
+  // ---- upload the join index ----
+  CKS(upload(ex, ex->uid_count, h_count));
+  CKS(upload(ex, ex->uid_loc, h_loc));
+  CKS(upload(ex, ex->uid_prefix, h_prefix));
+  CKS(upload(ex, ex->uid_res, h_res));
+  CKS(ex->signs.ensure(std::max<size_t>(n_signs, 1) * 4));
+  if (n_signs) CK(cudaMemcpyAsync(ex->signs.p, signs, (size_t)n_signs * 4, cudaMemcpyHostToDevice, ex->stream));
+
+  CK(cudaMemsetAsync(ex->d_perm_max, 0, (size_t)ex->Ip * 4, ex->stream));
+  CK(cudaMemsetAsync(ex->d_scalars, 0, 2 * sizeof(unsigned), ex->stream));
+
+  JoinParams jp;
+  memset(&jp, 0, sizeof jp);
+  jp.p0 = paths0->d_rows;
+  jp.p1 = paths1->d_rows;
+  jp.pres = keep ? paths_res->d_rows : nullptr;
+  jp.Wp = ex->Wp;
+  jp.n_cases = ex->n_cases;
+  jp.count = (const int32_t*)ex->uid_count.p;
+  jp.location = (const uint32_t*)ex->uid_loc.p;
+  jp.prefix = (const unsigned long long*)ex->uid_prefix.p;
+  jp.res_idx = (const unsigned long long*)ex->uid_res.p;
+  jp.n_uids = n_uids;
+  jp.signs = (const int32_t*)ex->signs.p;
+  jp.path_length = path_length;
+  jp.pm = ex->d_pm;
+  jp.pt = ex->d_pt;
+  jp.Ip = ex->Ip;
+  jp.Iw = ex->Iw;
+  jp.n_perm_tiles = ex->Ip / dense::TI;
+  jp.diagD = ex->d_diagD;
+  jp.diagF = ex->d_diagF;
+  jp.diagDM = ex->d_diagDM;
+  jp.perm_max = ex->d_perm_max;
+  jp.cand_count = ex->d_scalars;
+  jp.max_total = ex->d_scalars + 1;
+
+  // ---- chunked launches; candidates merged on the host between chunks ----
+  const unsigned long long chunk_max = 4ull << 20;
+  unsigned long long chunk = 64ull << 10;
+  std::vector<gcre_score> held;
+  std::vector<Cand> h_cand;
+  unsigned long long thr_key = score_key(-std::numeric_limits<double>::infinity());
+  double kernel_ms = 0.0;
+  int launches = 0;
+  for (unsigned long long p = pair_lo; p < pair_hi;) {
+    const unsigned long long pe = std::min(pair_hi, p + chunk);
+    const unsigned cap = (unsigned)(pe - p);
+    CKS(ex->cand.ensure((size_t)cap * sizeof(Cand)));
+    jp.cand = (Cand*)ex->cand.p;
+    jp.cand_cap = cap;
+    jp.thr_key = thr_key;
+    jp.pair_begin = p;
+    jp.pair_end = pe;
+    CK(cudaMemsetAsync(ex->d_scalars, 0, sizeof(unsigned), ex->stream));
+    CK(cudaEventRecord(ex->ev0, ex->stream));
+    CKS(launch_join(ex, jp, keep, kernel, &launches));
+    CK(cudaEventRecord(ex->ev1, ex->stream));
+    CK(cudaMemcpyAsync(ex->h_scalars, ex->d_scalars, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaStreamSynchronize(ex->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ex->ev0, ex->ev1));
+    kernel_ms += ms;
+    const unsigned n_cand = std::min(ex->h_scalars[0], cap);
+    if (n_cand) {
+      h_cand.resize(n_cand);
+      CK(cudaMemcpyAsync(h_cand.data(), ex->cand.p, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, ex->stream));
+      CK(cudaStreamSynchronize(ex->stream));
+      for (unsigned k = 0; k < n_cand; k++) {
+        gcre_score s;
+        s.score = key_score(h_cand[k].key);
+        s.src = (int32_t)h_cand[k].idx;
+        s.trg = (int32_t)h_cand[k].loc;
+        s.cases = h_cand[k].cases;
+        s.ctrls = h_cand[k].ctrls;
+        held.push_back(s);
+      }
+      trim_topk(held, top_k);
+      if ((int)held.size() == top_k) {
+        double kth = held[0].score;
+        for (const auto& s : held) kth = std::min(kth, s.score);
+        // later chunks hold larger (src, trg) only, so a tie with the K-th score can no longer win a place
+        thr_key = score_key(kth);
+      }
+    }
+    p = pe;
+    chunk = std::min(chunk * 8, chunk_max);
+  }
+  if (keep) paths_res->max_half_pop = (pair_lo == 0 && pair_hi == total) ? (long long)ex->h_scalars[1] : -1;
+
+  CKS(emit_topk(held, top_k, out_scores, n_scores));
+  if (out_perm && !(opts && opts->skip_host_perm)) CKS(gcre_exec_read_perm_max(ex, out_perm));
+  if (opts) {
+    opts->pairs_scored = pair_hi - pair_lo;
+    opts->kernel_ms = kernel_ms;
+    opts->kernel_used = kernel;
+    opts->launches = launches;
+  }
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_device_perm_max(const gcre_exec* ex, void** device_ptr, int* n_floats) {
+  if (!ex || !device_ptr || !n_floats) return fail(GCRE_ERR_ARG, "null argument");
+  *device_ptr = ex->d_perm_max;
+  *n_floats = ex->Ip;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_export_perm_max(const gcre_exec* ex, void* device_dst, int count) {
+  if (!ex || !device_dst) return fail(GCRE_ERR_ARG, "null argument");
+  if (count < 0 || count > ex->Ip) return fail(GCRE_ERR_RANGE, "assertion");
+  CKS(use_device(ex));
+  CK(cudaMemcpyAsync(device_dst, ex->d_perm_max, (size_t)count * 4, cudaMemcpyDeviceToDevice, ex->stream));
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_import_perm_max(gcre_exec* ex, const void* device_src, int count) {
+  if (!ex || !device_src) return fail(GCRE_ERR_ARG, "null argument");
+  if (count < 0 || count > ex->Ip) return fail(GCRE_ERR_RANGE, "assertion");
+  CKS(use_device(ex));
+  CK(cudaMemcpyAsync(ex->d_perm_max, device_src, (size_t)count * 4, cudaMemcpyDeviceToDevice, ex->stream));
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_read_perm_max(const gcre_exec* ex, double* out_perm) {
+  if (!ex || (!out_perm && ex->iters)) return fail(GCRE_ERR_ARG, "null argument");
+  CKS(use_device(ex));
+  if (!ex->iters) return GCRE_OK;
+  std::vector<float> h(ex->iters);
+  CK(cudaMemcpyAsync(h.data(), ex->d_perm_max, (size_t)ex->iters * 4, cudaMemcpyDeviceToHost, ex->stream));
+  CK(cudaStreamSynchronize(ex->stream));
+  for (int r = 0; r < ex->iters; r++) out_perm[r] = (double)h[r];  // src/join_base.cpp:145-146
+  return GCRE_OK;
+}

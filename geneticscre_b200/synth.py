@@ -36,7 +36,7 @@ def make_cohort_bits(n_patients: int, n_genes: int, seed: int, max_freq: float =
     n, w = int(n_patients), words_for(n_patients)
     bits = np.zeros((n_genes, w), dtype=np.uint64)
     cap = int(np.floor(max_freq * (n + 1)))
-    freq = np.exp(rng.uniform(np.log(1.0 / n), np.log(max_freq), size=n_genes))
+    freq = np.exp(rng.uniform(np.log(min(1.0 / n, max_freq)), np.log(max_freq), size=n_genes))
     k = np.minimum(rng.binomial(n, freq), cap)
     k[rng.random(n_genes) < zero_frac] = 0
     for g in np.nonzero(k)[0]:
@@ -203,11 +203,20 @@ def make_network(n_genes: int, n_edges: int, seed: int, tail: float = 1.2, max_p
     order = np.lexsort((pairs[:, 1], pairs[:, 0]))
     pairs = pairs[order]
     sign = np.where(rng.random(pairs.shape[0]) < 0.7, 1, -1).astype(np.int32)
-    g = int(used.shape[0])
-    src = pairs[:, 0].astype(np.int32)
-    trg = pairs[:, 1].astype(np.int32)
-    net = Network(n_genes=g, edges_src=src, edges_trg=trg, edges_sign=sign, ents2=np.unique(src).astype(np.int32))
+    net = network_from_edges(int(used.shape[0]), pairs[:, 0], pairs[:, 1], sign, max_path_length=max_path_length)
     net.used_genes = used.astype(np.int64)  # rows of the original cohort that became Ents rows
+    return net
+
+
+def network_from_edges(n_genes: int, src, trg, sign, ents2=None, max_path_length: int = 5) -> Network:
+    """Build the join indices for a given edge list (already unique, self-loop free, sorted by (src, trg))."""
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    trg = np.ascontiguousarray(trg, dtype=np.int32)
+    sign = np.ascontiguousarray(sign, dtype=np.int32)
+    if ents2 is None:
+        ents2 = np.unique(src)
+    net = Network(n_genes=int(n_genes), edges_src=src, edges_trg=trg, edges_sign=sign, ents2=np.ascontiguousarray(ents2, dtype=np.int32))
+    net.used_genes = np.arange(n_genes, dtype=np.int64)
     _derive_levels(net, max_path_length)
     return net
 

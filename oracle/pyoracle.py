@@ -74,6 +74,28 @@ def build(verbose: bool = False) -> None:
 
 _ptr = lambda a, t: a.ctypes.data_as(C.POINTER(t))
 
+_libc = C.CDLL(None)
+
+
+class _quiet_c_stdout:
+    """The reference printf()s progress lines to C stdout on every join (src/join_base.cpp:166-181); keep them out of
+    the caller's stdout (bench.py must print exactly one JSON line)."""
+
+    def __enter__(self):
+        import sys
+
+        sys.stdout.flush()
+        _libc.fflush(None)
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *exc):
+        _libc.fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
 
 def _as(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
@@ -203,7 +225,9 @@ class RefExec:
 
     def setPermutedCases(self, perms):
         p = _as(perms, np.int32)
-        if self.lib.ref_exec_set_perms(self.h, _ptr(p, C.c_int), p.shape[0], p.shape[1] if p.ndim == 2 else 0) != 0:
+        with _quiet_c_stdout():
+            rc = self.lib.ref_exec_set_perms(self.h, _ptr(p, C.c_int), p.shape[0], p.shape[1] if p.ndim == 2 else 0)
+        if rc != 0:
             raise RuntimeError("reference perms: " + self.lib.ref_last_error().decode())
 
     def setPermutedMasks(self, masks):
@@ -221,9 +245,10 @@ class RefExec:
         cap = self._top_k + 1
         sc = (_ScoreC * cap)()
         perm = np.zeros(max(self.iters, 1), dtype=np.float64)
-        n = self.lib.ref_join(self.h, uids.path_length, uids.size(), _ptr(uids.src, C.c_int), _ptr(uids.trg, C.c_int),
-                              _ptr(uids.count, C.c_int), _ptr(uids.location, C.c_uint), _ptr(uids.signs, C.c_int),
-                              uids.signs.shape[0], paths0.h, paths1.h, paths_res.h, sc, cap, _ptr(perm, C.c_double))
+        with _quiet_c_stdout():
+            n = self.lib.ref_join(self.h, uids.path_length, uids.size(), _ptr(uids.src, C.c_int), _ptr(uids.trg, C.c_int),
+                                  _ptr(uids.count, C.c_int), _ptr(uids.location, C.c_uint), _ptr(uids.signs, C.c_int),
+                                  uids.signs.shape[0], paths0.h, paths1.h, paths_res.h, sc, cap, _ptr(perm, C.c_double))
         if n < 0:
             raise RuntimeError("reference join: " + self.lib.ref_last_error().decode())
         return JoinedRes([Score(s.score, s.src, s.trg, s.cases, s.ctrls) for s in sc[:n]], perm[: self.iters].copy())

@@ -1,0 +1,58 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gcre_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcre_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(engine):
+    from geneticscre_b200 import _lib
+
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/gcre_b200.h but not exported"
+    assert set(names) == set(_lib.SYMBOLS), "ctypes binding and header disagree"
+
+
+def test_no_cpu_fallback(engine):
+    """Without a CUDA device the engine must refuse to run, not fall back."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from geneticscre_b200 import _lib
+
+    with pytest.raises(_lib.GcreError):
+        engine.JoinExec("method1", 10, 10, 4)
+
+
+def test_merge_topk_rule(engine):
+    S = engine.Score
+    merged = engine.merge_topk([[S(1.0, 5, 1, 1, 1), S(2.0, 3, 2, 1, 1)], [S(float("-inf"), -1, -1, 0, 0), S(2.0, 0, 9, 1, 1)]], 2)
+    assert [(s.score, s.src, s.trg) for s in merged] == [(2.0, 3, 2), (2.0, 0, 9)]
+    merged = engine.merge_topk([[S(1.0, 5, 1, 1, 1)]], 3)
+    assert [(s.score, s.src) for s in merged] == [(float("-inf"), -1), (1.0, 5)]
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (checked textually over the package and headers)."""
+    bad = []
+    for base in ("geneticscre_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "gcre_oracle" in txt or "pyoracle" in txt:
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

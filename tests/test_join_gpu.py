@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle on identical seeded inputs.
+
+Integer counts, kept path-set words, f64 scores and f32-rounded permutation maxima must be bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import helpers
+from geneticscre_b200 import _lib, synth
+from test_oracle import GOLDENS, _kat, check_kat
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [_lib.KERNEL_DENSE, _lib.KERNEL_SPARSE]
+
+
+def run_engine(engine, w, method, path_length, top_k, kernel, **kw):
+    class Exec(engine.JoinExec):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.kernel = kernel
+
+    return helpers.run_schedule(Exec, engine.UidRelSet, w, method, path_length, top_k, **kw)
+
+
+@pytest.mark.parametrize("method,sign", [("method1", 1), ("method1", -1), ("method2", 1), ("method2", -1)])
+def test_known_answer(engine, method, sign):
+    check_kat(_kat(engine.JoinExec, engine.UidRelSet, method, sign), method, sign)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", GOLDENS)
+def test_golden_fixtures(engine, oracles, name, kernel):
+    """BASELINE configs 1 and 2 (vignette data) + a synthetic 5-level case against outputs of the reference itself."""
+    w, method, path_length, top_k, want, kept_want = helpers.load_golden(name)
+    res, kept, _ = run_engine(engine, w, method, path_length, top_k, kernel)
+    for k in kept_want:
+        assert np.array_equal(kept[k], kept_want[k]), f"kept {k} differs"
+    for lvl in want:
+        oracles.compare_results(res[lvl], want[lvl], recompute=helpers.make_recompute(w, method, kept, lvl), what=f"{name} L{lvl}")
+
+
+SHAPES = [
+    # n_cases, n_ctrls, genes, edges, perms, top_k
+    (4, 4, 30, 60, 1, 3),
+    (32, 32, 60, 150, 128, 5),        # n = 64: one exact word, perms = one full tile
+    (64, 64, 80, 200, 129, 7),        # n = 128: even word count, perms one over a tile
+    (100, 93, 150, 500, 100, 10),     # W64 = 4 (vignette-like)
+    (257, 300, 200, 800, 257, 12),    # W64 = 9 (odd -> padded to 10)
+    (700, 724, 120, 420, 40, 4),      # W64 = 23, several k-chunks
+]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("method", ["method1", "method2"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_schedule_matches_oracle(engine, oracles, method, shape, kernel):
+    nc, nt, g, e, perms, top_k = shape
+    w = synth.make_workload(nc, nt, g, e, perms, seed=1000 + nc + perms, max_path_length=5, real_table=(nc % 2 == 0),
+                            max_freq=0.12, zero_frac=0.3)
+    want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 5, top_k)
+    got, kept, _ = run_engine(engine, w, method, 5, top_k, kernel)
+    for k in kept_want:
+        assert np.array_equal(kept[k], kept_want[k]), f"kept {k} differs"
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} {shape} L{lvl}")
+
+
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_int_matrix_inputs(engine, oracles, method):
+    """The R-facing formats: IntegerMatrix data (PathSet::load) and CaseORControl (setPermutedCases)."""
+    w = synth.make_workload(90, 110, 100, 300, 50, seed=77, max_path_length=4, real_table=True, max_freq=0.1, zero_frac=0.2)
+    want, kw, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, 6, use_int_matrices=True, int_perms=True)
+    got, kg, _ = helpers.run_schedule(engine.JoinExec, engine.UidRelSet, w, method, 4, 6, use_int_matrices=True, int_perms=True)
+    for k in kw:
+        assert np.array_equal(kg[k], kw[k])
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
+
+
+@pytest.mark.parametrize("rows", [3, 20])
+def test_perm_rows_reused_or_truncated(engine, oracles, rows):
+    """Fewer perm rows than iterations are reused cyclically, surplus rows ignored (src/join_base.cpp:89-90,116-123)."""
+    nc, nt, iters = 20, 30, 8
+    w = synth.make_workload(nc, nt, 40, 100, iters, seed=5, max_path_length=2, real_table=True, max_freq=0.2, zero_frac=0.1)
+    perm = synth.make_perm_matrix(nc, nt, rows, seed=9)
+    out = []
+    for cls, ucls in ((oracles.OracleExec, oracles.UidRelSet), (engine.JoinExec, engine.UidRelSet)):
+        ex = cls("method1", nc, nt, iters)
+        ex.top_k = 5
+        ex.setValueTable(w.value_table)
+        ex.setPermutedCases(perm)
+        p1 = ex.createPathSet(w.net.n_genes)
+        p1.load_bits(w.gene_bits)
+        lv = w.net.levels["1a"]
+        out.append(ex.join(ucls(1, lv.src, lv.trg, lv.count, lv.location, lv.signs), ex.createPathSet(lv.n_uids), p1, ex.createPathSet(0)))
+    helpers.assert_same_results(out[1], out[0])
+
+
+def test_zero_iterations_and_small_topk(engine, oracles):
+    """iterations = 0 is legal (test/issue-019.r); fewer pairs than top_k leaves the -inf sentinel in front."""
+    w = synth.make_workload(10, 12, 12, 20, 0, seed=3, max_path_length=3, real_table=True, max_freq=0.3, zero_frac=0.0)
+    want, _, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, "method2", 3, 1000)
+    got, _, _ = helpers.run_schedule(engine.JoinExec, engine.UidRelSet, w, "method2", 3, 1000)
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=lvl)
+        assert got[lvl].scores[0].src == -1 and got[lvl].scores[0].score == -math.inf
+        assert got[lvl].permuted_scores.shape == (0,)
+
+
+def test_prechecks_raise_like_reference(engine):
+    """src/join_base.cpp:196-200 -> logic_error / out_of_range ("assertion")."""
+    ex = engine.JoinExec("method1", 5, 5, 4)
+    ex.setValueTable(np.zeros((6, 6)))
+    ex.setPermutedMasks(np.zeros((4, 1), dtype=np.uint64))
+    p0, p1 = ex.createPathSet(3), ex.createPathSet(2)
+    U = engine.UidRelSet
+    with pytest.raises(_lib.GcreAssertion):  # uids.size() != paths0.size
+        ex.join(U(2, [0, 0], [0, 0], [1, 1], [0, 0], [1, 1]), p0, p1, ex.createPathSet(0))
+    with pytest.raises(_lib.GcreOutOfRange):  # location + count - 1 >= paths1.size
+        ex.join(U(2, [0] * 3, [0] * 3, [1, 2, 0], [0, 1, 0], [1, 1]), p0, p1, ex.createPathSet(0))
+    with pytest.raises(_lib.GcreAssertion):  # paths_res.size not in {0, total}
+        ex.join(U(2, [0] * 3, [0] * 3, [1, 1, 0], [0, 1, 0], [1, 1]), p0, p1, ex.createPathSet(5))
+    with pytest.raises(_lib.GcreAssertion):  # PathSet::load row-count check (src/gcre_paths.h:60)
+        p0.load(np.zeros((2, 10), dtype=np.int32))
+    with pytest.raises(_lib.GcreOutOfRange):  # PathSet::select index check (src/gcre_paths.h:85)
+        p0.select([0, 3])
+    with pytest.raises(_lib.GcreAssertion):  # JoinExec ctor check (src/join_base.cpp:47)
+        engine.JoinExec("method1", 0, 5, 4)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_sharded_join_merges_to_full(engine, oracles, method, kernel):
+    """Upstream-row shards merged by max / top-K merge equal the unsharded join (the multi-GPU decomposition)."""
+    w = synth.make_workload(120, 130, 150, 600, 70, seed=21, max_path_length=4, real_table=True, max_freq=0.1, zero_frac=0.3)
+    want, _, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, 8)
+    ex = engine.JoinExec(method, w.n_cases, w.n_ctrls, w.n_perms)
+    ex.kernel = kernel
+    ex.top_k = 8
+    ex.setValueTable(w.value_table)
+    ex.setPermutedMasks(w.perm_masks)
+    from geneticscre_b200 import schedule
+
+    _, kept = schedule.replay_levels(ex, engine.UidRelSet, w, 3)
+    lv = w.net.levels["4"]
+    uids = engine.UidRelSet(4, lv.src, lv.trg, lv.count, lv.location, lv.signs)
+    cuts = [0, lv.n_uids // 3, lv.n_uids // 3, (2 * lv.n_uids) // 3, lv.n_uids]  # includes an empty shard
+    parts = [ex.join(uids, kept["paths3"], kept["paths2"], ex.createPathSet(0), uid_range=(a, b)) for a, b in zip(cuts[:-1], cuts[1:]) if True]
+    perm = np.max(np.stack([p.permuted_scores for p in parts]), axis=0)
+    merged = engine.joined_res(engine.merge_topk([p.scores for p in parts], 8), perm)
+    helpers.assert_same_results(merged, want["4"], what="sharded")
+    assert sum(p.info["pairs"] for p in parts) == lv.n_pairs
+
+
+def test_pathset_row_access(engine):
+    ex = engine.JoinExec("method2", 40, 37, 1)
+    ps = ex.createPathSet(3)
+    row = np.arange(4, dtype=np.uint64) + np.uint64(1 << 40)
+    ps.set(1, row)
+    assert np.array_equal(ps[1], row)
+    assert not ps[0].any()
+    sel = ps.select([1, 1, 2])
+    assert np.array_equal(sel.to_numpy(), np.stack([row, row, np.zeros(4, np.uint64)]))
+    with pytest.raises(IndexError):
+        ps[3]
