@@ -95,8 +95,8 @@ struct gcre_exec {
   long long diag_cap = -1;
   // outputs / scratch
   int* d_perm_max = nullptr;
-  unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total
-  DevBuf cand, uid_count, uid_loc, uid_prefix, uid_res, signs, scratch;
+  unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total, [2..3] 64-bit work counter of the sparse kernel
+  DevBuf cand, uid_count, uid_loc, uid_prefix, uid_res, uid_units, signs, scratch, scan_tmp;
   unsigned* h_scalars = nullptr;  // pinned
 };
 
@@ -105,7 +105,16 @@ struct gcre_pathset {
   uint32_t size = 0;
   uint64_t* d_rows = nullptr;
   long long max_half_pop = 0;  // max carriers in any half-row; -1 = unknown (recomputed on demand)
+  SparseView view;             // carrier lists, built on first use by a sparse join
 };
+
+static void drop_view(gcre_pathset* ps) {
+  cudaStream_t st = ps->ex->stream;
+  if (ps->view.off) cudaFreeAsync(ps->view.off, st);
+  if (ps->view.car) cudaFreeAsync(ps->view.car, st);
+  if (ps->view.ncase) cudaFreeAsync(ps->view.ncase, st);
+  ps->view = SparseView();
+}
 
 static int use_device(const gcre_exec* ex) {
   CK(cudaSetDevice(ex->device));
@@ -157,6 +166,13 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
   int rc = [&]() -> int {
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&ex->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {
+      // stream-ordered allocations (path sets, carrier-list views) come from the device pool and stay cached in it
+      cudaMemPool_t pool;
+      CK(cudaDeviceGetDefaultMemPool(&pool, device));
+      unsigned long long keep_all = ~0ull;
+      CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+    }
     CK(cudaStreamCreateWithFlags(&ex->own_stream, cudaStreamNonBlocking));
     ex->stream = ex->own_stream;
     CK(cudaEventCreate(&ex->ev0));
@@ -200,6 +216,8 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   ex->uid_loc.release();
   ex->uid_prefix.release();
   ex->uid_res.release();
+  ex->uid_units.release();
+  ex->scan_tmp.release();
   ex->signs.release();
   ex->scratch.release();
   if (ex->ev0) cudaEventDestroy(ex->ev0);
@@ -336,14 +354,14 @@ extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_path
   ps->size = size;
   const size_t bytes = (size_t)size * row_words(ex) * 8;
   if (bytes) {
-    cudaError_t e = cudaMalloc(&ps->d_rows, bytes);
+    cudaError_t e = cudaMallocAsync(&ps->d_rows, bytes, ex->stream);
     if (e != cudaSuccess) {
       delete ps;
-      return fail(GCRE_ERR_NOMEM, "cudaMalloc of %zu bytes for a path set failed: %s", bytes, cudaGetErrorString(e));
+      return fail(GCRE_ERR_NOMEM, "cudaMallocAsync of %zu bytes for a path set failed: %s", bytes, cudaGetErrorString(e));
     }
     e = cudaMemsetAsync(ps->d_rows, 0, bytes, ex->stream);
     if (e != cudaSuccess) {
-      cudaFree(ps->d_rows);
+      cudaFreeAsync(ps->d_rows, ex->stream);
       delete ps;
       return fail(GCRE_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
@@ -355,8 +373,8 @@ extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_path
 extern "C" int gcre_pathset_destroy(gcre_pathset* ps) {
   if (!ps) return GCRE_OK;
   cudaSetDevice(ps->ex->device);
-  cudaStreamSynchronize(ps->ex->stream);
-  cudaFree(ps->d_rows);
+  if (ps->d_rows) cudaFreeAsync(ps->d_rows, ps->ex->stream);  // stream-ordered: no host synchronisation
+  drop_view(ps);
   delete ps;
   return GCRE_OK;
 }
@@ -412,6 +430,7 @@ extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint
     CK(cudaStreamSynchronize(ex->stream));
   }
   ps->max_half_pop = -1;
+  drop_view(ps);
   return GCRE_OK;
 }
 
@@ -434,6 +453,7 @@ extern "C" int gcre_pathset_load_bits(gcre_pathset* ps, const uint64_t* bits, ui
     CK(cudaStreamSynchronize(ex->stream));
   }
   ps->max_half_pop = -1;
+  drop_view(ps);
   return GCRE_OK;
 }
 
@@ -479,6 +499,7 @@ extern "C" int gcre_pathset_set_row(gcre_pathset* ps, uint32_t idx, const uint64
                        cudaMemcpyHostToDevice, ex->stream));
   CK(cudaStreamSynchronize(ex->stream));
   ps->max_half_pop = -1;
+  drop_view(ps);
   return GCRE_OK;
 }
 
@@ -592,6 +613,44 @@ extern "C" int gcre_merge_topk(const gcre_score* lists, const int* list_sizes, i
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// carrier-list views for the sparse kernels
+// ------------------------------------------------------------------------------------------------------------------
+static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
+  if (ps->view.valid) return GCRE_OK;
+  drop_view(ps);
+  const long long items = (long long)ps->size * ex->M;
+  CK(cudaMallocAsync(&ps->view.off, (size_t)(items + 1) * 4, ex->stream));
+  CK(cudaMallocAsync(&ps->view.ncase, std::max<size_t>(items, 1) * 4, ex->stream));
+  CK(cudaMemsetAsync(ps->view.off, 0, (size_t)(items + 1) * 4, ex->stream));
+  uint32_t total = 0;
+  if (items > 0) {
+    // counts -> exclusive offsets (cub scan over items + 1 entries, the last input is 0)
+    CKS(ex->scratch.ensure((size_t)(items + 1) * 4));
+    uint32_t* cnt = (uint32_t*)ex->scratch.p;
+    CK(cudaMemsetAsync(cnt, 0, (size_t)(items + 1) * 4, ex->stream));
+    half_popcount_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, cnt);
+    CK(cudaGetLastError());
+    LAUNCHED();
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, ps->view.off, (int)(items + 1), ex->stream));
+    CKS(ex->scan_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceScan::ExclusiveSum(ex->scan_tmp.p, tmp_bytes, cnt, ps->view.off, (int)(items + 1), ex->stream));
+    LAUNCHED();
+    CK(cudaMemcpyAsync(&total, ps->view.off + items, 4, cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaStreamSynchronize(ex->stream));
+  }
+  CK(cudaMallocAsync(&ps->view.car, std::max<size_t>(total, 1) * 2, ex->stream));
+  if (items > 0) {
+    build_lists_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ps->view.off, ps->view.car, ps->view.ncase);
+    CK(cudaGetLastError());
+    LAUNCHED();
+  }
+  ps->view.total = total;
+  ps->view.valid = true;
+  return GCRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // join
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -601,10 +660,9 @@ static int upload(gcre_exec* ex, DevBuf& buf, const std::vector<T>& v) {
   return GCRE_OK;
 }
 
-static int launch_join(gcre_exec* ex, const JoinParams& jp, bool keep, int kernel, int* launches) {
+static int launch_join_dense(gcre_exec* ex, const JoinParams& jp, bool keep, int* launches) {
   const unsigned long long n_pairs = jp.pair_end - jp.pair_begin;
   if (n_pairs == 0) return GCRE_OK;
-  if (kernel == GCRE_KERNEL_SPARSE) return launch_join_sparse(ex->stream, jp, ex->M, keep, ex->sm_count, launches);
   const unsigned long long tiles = (n_pairs + dense::TP - 1) / dense::TP;
   const unsigned long long blocks = tiles * jp.n_perm_tiles;
   if (blocks > 0x7fffffffull) return fail(GCRE_ERR_ARG, "join chunk too large");
@@ -678,9 +736,31 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
 
   // ---- kernel choice ----
   int kernel = opts ? opts->kernel : GCRE_KERNEL_AUTO;
-  if (kernel != GCRE_KERNEL_DENSE && kernel != GCRE_KERNEL_SPARSE) kernel = sparse_supported(ex->n, t_needed) ? GCRE_KERNEL_SPARSE : GCRE_KERNEL_DENSE;
-  if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed)) kernel = GCRE_KERNEL_DENSE;
-  if (kernel == GCRE_KERNEL_SPARSE) CKS(ensure_patient_major(ex));
+  if (kernel != GCRE_KERNEL_DENSE && kernel != GCRE_KERNEL_SPARSE)
+    kernel = sparse_supported(ex->n, t_needed, ex->iters) ? GCRE_KERNEL_SPARSE : GCRE_KERNEL_DENSE;
+  // an explicit request for the sparse kernel is honoured whenever its index widths allow (also with few permutations)
+  if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, 1 << 30)) kernel = GCRE_KERNEL_DENSE;
+  SparseParams sp;
+  memset(&sp, 0, sizeof sp);
+  std::vector<unsigned long long> h_units;
+  if (kernel == GCRE_KERNEL_SPARSE) {
+    CKS(ensure_patient_major(ex));
+    CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths0)));
+    CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths1)));
+    h_units.resize((size_t)n_uids + 1);
+    unsigned long long nu = 0;
+    for (uint32_t u = 0; u < n_uids; u++) {
+      h_units[u] = nu;
+      nu += ((unsigned long long)h_count[u] + sparse::PB - 1) / sparse::PB;
+    }
+    h_units[n_uids] = nu;
+    CKS(upload(ex, ex->uid_units, h_units));
+    sp.off0 = paths0->view.off; sp.car0 = paths0->view.car; sp.ncase0 = paths0->view.ncase;
+    sp.off1 = paths1->view.off; sp.car1 = paths1->view.car; sp.ncase1 = paths1->view.ncase;
+    sp.unit_prefix = (const unsigned long long*)ex->uid_units.p;
+    sp.work_counter = (unsigned long long*)(ex->d_scalars + 2);
+    sp.n_perm_blocks = (ex->Iw + 31) / 32;
+  }
 
   // ---- upload the join index ----
   CKS(upload(ex, ex->uid_count, h_count));
@@ -720,25 +800,38 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   jp.max_total = ex->d_scalars + 1;
 
   // ---- chunked launches; candidates merged on the host between chunks ----
-  const unsigned long long chunk_max = 4ull << 20;
-  unsigned long long chunk = 64ull << 10;
+  // dense kernel: chunks are ranges of flattened pairs; sparse kernel: ranges of units (<= PB pairs each)
+  const bool sparse_k = kernel == GCRE_KERNEL_SPARSE;
+  const unsigned long long per_item = sparse_k ? sparse::PB : 1;
+  const unsigned long long item_lo = sparse_k ? h_units[ub] : pair_lo, item_hi = sparse_k ? h_units[ue] : pair_hi;
+  const unsigned long long chunk_max = (4ull << 20) / per_item;
+  unsigned long long chunk = (64ull << 10) / per_item;
   std::vector<gcre_score> held;
   std::vector<Cand> h_cand;
   unsigned long long thr_key = score_key(-std::numeric_limits<double>::infinity());
   double kernel_ms = 0.0;
   int launches = 0;
-  for (unsigned long long p = pair_lo; p < pair_hi;) {
-    const unsigned long long pe = std::min(pair_hi, p + chunk);
-    const unsigned cap = (unsigned)(pe - p);
+  for (unsigned long long p = item_lo; p < item_hi;) {
+    const unsigned long long pe = std::min(item_hi, p + chunk);
+    const unsigned cap = (unsigned)((pe - p) * per_item);
     CKS(ex->cand.ensure((size_t)cap * sizeof(Cand)));
     jp.cand = (Cand*)ex->cand.p;
     jp.cand_cap = cap;
     jp.thr_key = thr_key;
-    jp.pair_begin = p;
-    jp.pair_end = pe;
     CK(cudaMemsetAsync(ex->d_scalars, 0, sizeof(unsigned), ex->stream));
     CK(cudaEventRecord(ex->ev0, ex->stream));
-    CKS(launch_join(ex, jp, keep, kernel, &launches));
+    if (sparse_k) {
+      sp.unit_begin = p;
+      sp.n_units = pe - p;
+      CK(cudaMemsetAsync(ex->d_scalars + 2, 0, 2 * sizeof(unsigned), ex->stream));
+      CK(launch_join_sparse(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
+      LAUNCHED();
+      launches++;
+    } else {
+      jp.pair_begin = p;
+      jp.pair_end = pe;
+      CKS(launch_join_dense(ex, jp, keep, &launches));
+    }
     CK(cudaEventRecord(ex->ev1, ex->stream));
     CK(cudaMemcpyAsync(ex->h_scalars, ex->d_scalars, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ex->stream));
     CK(cudaStreamSynchronize(ex->stream));
@@ -751,18 +844,18 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
       CK(cudaMemcpyAsync(h_cand.data(), ex->cand.p, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, ex->stream));
       CK(cudaStreamSynchronize(ex->stream));
       for (unsigned k = 0; k < n_cand; k++) {
-        gcre_score s;
-        s.score = key_score(h_cand[k].key);
-        s.src = (int32_t)h_cand[k].idx;
-        s.trg = (int32_t)h_cand[k].loc;
-        s.cases = h_cand[k].cases;
-        s.ctrls = h_cand[k].ctrls;
-        held.push_back(s);
+        gcre_score sc;
+        sc.score = key_score(h_cand[k].key);
+        sc.src = (int32_t)h_cand[k].idx;
+        sc.trg = (int32_t)h_cand[k].loc;
+        sc.cases = h_cand[k].cases;
+        sc.ctrls = h_cand[k].ctrls;
+        held.push_back(sc);
       }
       trim_topk(held, top_k);
       if ((int)held.size() == top_k) {
         double kth = held[0].score;
-        for (const auto& s : held) kth = std::min(kth, s.score);
+        for (const auto& sc : held) kth = std::min(kth, sc.score);
         // later chunks hold larger (src, trg) only, so a tie with the K-th score can no longer win a place
         thr_key = score_key(kth);
       }
@@ -770,7 +863,10 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
     p = pe;
     chunk = std::min(chunk * 8, chunk_max);
   }
-  if (keep) paths_res->max_half_pop = (pair_lo == 0 && pair_hi == total) ? (long long)ex->h_scalars[1] : -1;
+  if (keep) {
+    paths_res->max_half_pop = (pair_lo == 0 && pair_hi == total) ? (long long)ex->h_scalars[1] : -1;
+    drop_view(paths_res);
+  }
 
   CKS(emit_topk(held, top_k, out_scores, n_scores));
   if (out_perm && !(opts && opts->skip_host_perm)) CKS(gcre_exec_read_perm_max(ex, out_perm));

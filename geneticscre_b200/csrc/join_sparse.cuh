@@ -1,11 +1,381 @@
-// Sparse (carrier-list) join kernels -- placeholder until the dense path is parity-green on the GPU.
+// Sparse join + permutation scoring (sm_100a): carrier-list walk over patient-major permutation masks.
+//
+// Rare-variant rows are sparse (R keeps genes with carriers <= 5 % of patients, R/Utils.R:185-188), so instead of
+// AND+POPC over all W words per permutation (src/methods.h:73-88) the count |joined & mask_r| is formed as
+//        sum over carriers c of the joined row of  PT[c][r]          (PT = permutation masks, patient-major bits)
+// with 32 permutations per 32-bit word held in bit-sliced (vertical) counters: one LOP3 pair (carry-save adder) adds
+// one carrier to 32 permutations at once.  The counts are exact integers, so every result is bit-identical to the
+// dense formulation and to the reference.
+//
+// Work decomposition (one warp = one "unit" at a time, lanes = 32 permutation words = 1,024 permutations):
+//   unit  = (upstream row idx, a block of <= PB of its partners, a block of 1,024 permutations)
+//   base  : the upstream row's own carriers are accumulated once per unit        -> base counts (u16, shared memory)
+//   pair  : only the partner's carriers NOT already in the upstream row (bit test against the dense upstream row) are
+//           accumulated on top of the base; partners that add no carrier reuse the base evaluation
+//   score : counts -> anti-diagonal value-table look-ups (src/methods.h:96-103, 220-230) -> running per-permutation
+//           max kept in registers across all units of the warp, merged at the end with one atomicMax per permutation
+//   true scores / top-K candidates / kept rows exactly as in the dense kernel.
 #pragma once
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 namespace gcre {
 
-static inline bool sparse_supported(int /*n*/, long long /*t_needed*/) { return false; }
+namespace sparse {
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int PB = 64;          // partners per unit
+constexpr int FLUSH_AT = 240;   // carriers accumulated in the 8 bit planes before they are flushed into u16 counters
+}  // namespace sparse
 
-static inline int launch_join_sparse(cudaStream_t, const JoinParams&, int, bool, int, int*) { return -3; }
+// Carrier-list (CSR) view of a path set: per (row, half) the ascending patient indices of its set bits.
+struct SparseView {
+  uint32_t* off = nullptr;    // [size*M + 1]
+  uint16_t* car = nullptr;    // [off[size*M]]
+  uint32_t* ncase = nullptr;  // [size*M] carriers < n_cases (a prefix of the ascending list)
+  size_t total = 0;
+  bool valid = false;
+};
+
+struct SparseParams {
+  const uint32_t* off0; const uint16_t* car0; const uint32_t* ncase0;
+  const uint32_t* off1; const uint16_t* car1; const uint32_t* ncase1;
+  const unsigned long long* unit_prefix;  // [U+1] running sum of ceil(count/PB)
+  unsigned long long unit_begin, n_units;  // units of this launch
+  unsigned long long* work_counter;
+  int n_perm_blocks;                      // ceil(Iw / 32)
+};
+
+// ---- view construction ----------------------------------------------------------------------------------------------
+__global__ void half_popcount_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, uint32_t* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= n_items) return;
+  const uint64_t* p = rows + (size_t)warp * Wp;
+  unsigned c = 0;
+  for (int k = lane; k < Wp; k += 32) c += __popcll(p[k]);
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0) cnt[warp] = c;
+}
+
+__global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, int n_cases, const uint32_t* __restrict__ off,
+                                   uint16_t* __restrict__ car, uint32_t* __restrict__ ncase) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= n_items) return;
+  const uint64_t* p = rows + (size_t)warp * Wp;
+  uint32_t pos = off[warp];
+  unsigned nc = 0;
+  for (int k0 = 0; k0 < Wp; k0 += 32) {
+    const int k = k0 + lane;
+    uint64_t w = (k < Wp) ? p[k] : 0ull;
+    const unsigned c = __popcll(w);
+    // exclusive prefix over lanes keeps the list ascending
+    unsigned incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    uint32_t o = pos + incl - c;
+    while (w) {
+      const int b = __ffsll((long long)w) - 1;
+      w &= w - 1;
+      const int patient = k * 64 + b;
+      car[o++] = (uint16_t)patient;
+      nc += patient < n_cases;
+    }
+    pos += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  nc = __reduce_add_sync(0xffffffffu, nc);
+  if (lane == 0) ncase[warp] = nc;
+}
+
+// ---- bit-sliced counters -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t u = a ^ b;
+  hi = (a & b) | (u & c);
+  lo = u ^ c;
+}
+
+// add eight 1-bit-per-permutation words into the 8 bit planes (Harley-Seal carry-save tree: 3 LOP3 per carrier)
+__device__ __forceinline__ void hs8(uint32_t (&pl)[8], const uint32_t (&x)[8]) {
+  uint32_t ta, tb, fa, fb, e;
+  csa(ta, pl[0], pl[0], x[0], x[1]);
+  csa(tb, pl[0], pl[0], x[2], x[3]);
+  csa(fa, pl[1], pl[1], ta, tb);
+  csa(ta, pl[0], pl[0], x[4], x[5]);
+  csa(tb, pl[0], pl[0], x[6], x[7]);
+  csa(fb, pl[1], pl[1], ta, tb);
+  csa(e, pl[2], pl[2], fa, fb);
+#pragma unroll
+  for (int j = 3; j < 8; j++) {
+    const uint32_t t = pl[j] & e;
+    pl[j] ^= e;
+    e = t;
+  }
+}
+
+// planes -> per-permutation counts, added into 16 registers of packed u16 pairs.
+// bit b of the lane's word (permutation b of the lane's 32): s = b & 7, q = b >> 3 -> register 2s + (q >> 1), half q & 1.
+__device__ __forceinline__ void flush_planes(uint32_t (&c16)[16], uint32_t (&pl)[8], int nbits) {
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    uint32_t r8 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (j < nbits) {
+        const uint32_t v = (s >= j) ? (pl[j] >> (s - j)) : (pl[j] << (j - s));
+        r8 |= v & (0x01010101u << j);
+      }
+    }
+    c16[2 * s] += __byte_perm(r8, 0u, 0x4140);
+    c16[2 * s + 1] += __byte_perm(r8, 0u, 0x4342);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) pl[j] = 0;
+}
+
+__device__ __forceinline__ int bits_for(int count) { return 32 - __clz(count); }  // count in [1, 255] -> 1..8
+
+// register index / half of permutation bit b inside the packed u16 counters
+#define GCRE_C16_REG(b) (2 * ((b) & 7) + ((b) >> 4))
+#define GCRE_C16_HI(b) (((b) >> 3) & 1)
+
+template <int M, bool KEEP>
+__global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const JoinParams a, const SparseParams s) {
+  using namespace sparse;
+  __shared__ uint32_t s_base[WARPS][M][16][32];  // base counts per warp / half / packed register / lane
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Wp = a.Wp, Iw = a.Iw;
+  const int row_words = Wp * M;
+  const unsigned long long n_work = s.n_units * (unsigned long long)s.n_perm_blocks;
+
+  float best[32];
+#pragma unroll
+  for (int b = 0; b < 32; b++) best[b] = 0.0f;
+  int pb_cur = -1;
+
+  auto flush_best = [&](int pb) {
+    const int r0 = (pb * 32 + lane) * 32;
+    if (pb * 32 + lane < Iw) {
+#pragma unroll
+      for (int b = 0; b < 32; b++)
+        if (best[b] > 0.0f) atomicMax(a.perm_max + r0 + b, __float_as_int(best[b]));
+    }
+  };
+
+  while (true) {
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(s.work_counter, 1ull);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= n_work) break;
+    const int pb = (int)(g / s.n_units);
+    const unsigned long long unit = s.unit_begin + (g % s.n_units);
+    if (pb != pb_cur) {
+      if (pb_cur >= 0) flush_best(pb_cur);
+#pragma unroll
+      for (int b = 0; b < 32; b++) best[b] = 0.0f;
+      pb_cur = pb;
+    }
+    const bool first_pb = (pb == 0);
+    const uint32_t idx = find_uid(s.unit_prefix, a.n_uids, unit);
+    const uint32_t sub = (uint32_t)(unit - s.unit_prefix[idx]);
+    const uint32_t cnt_idx = (uint32_t)a.count[idx];
+    const uint32_t j0 = sub * PB, j1 = min(cnt_idx, j0 + PB);
+    const bool w_ok = (pb * 32 + lane) < Iw;
+    const uint32_t* pt_lane = a.pt + pb * 32 + lane;
+    const uint64_t* p0row = a.p0 + (size_t)idx * row_words;
+
+    // accumulate carriers held one per lane (`c`, valid where bit set in `mask`) into the planes
+    uint32_t pl[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) pl[j] = 0;
+    int inbatch = 0;
+    auto add_masked = [&](uint32_t (&c16)[16], unsigned mask, uint32_t c) {
+      while (mask) {
+        uint32_t x[8];
+        int took = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const bool have = mask != 0;
+          const int src = have ? (__ffs((int)mask) - 1) : 0;
+          mask &= mask - 1;  // no-op on 0
+          const uint32_t cc = __shfl_sync(0xffffffffu, c, src);
+          x[q] = (have && w_ok) ? __ldg(pt_lane + (size_t)cc * Iw) : 0u;
+          took += have;
+        }
+        hs8(pl, x);
+        inbatch += took;
+        if (inbatch > FLUSH_AT) {
+          flush_planes(c16, pl, 8);
+          inbatch = 0;
+        }
+      }
+    };
+
+    // ---- base: the upstream row's own carriers ----
+    uint32_t t0[M], nc0[M];
+#pragma unroll
+    for (int h = 0; h < M; h++) {
+      uint32_t acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) acc[i] = 0;
+      const uint32_t o = s.off0[(size_t)idx * M + h], len = s.off0[(size_t)idx * M + h + 1] - o;
+      t0[h] = len;
+      nc0[h] = s.ncase0[(size_t)idx * M + h];
+      for (uint32_t i0 = 0; i0 < len; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t c = (i < len) ? s.car0[o + i] : 0u;
+        const unsigned mask = __ballot_sync(0xffffffffu, i < len);
+        add_masked(acc, mask, c);
+      }
+      if (inbatch > 0) {
+        flush_planes(acc, pl, bits_for(inbatch));
+        inbatch = 0;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i++) s_base[warp][h][i][lane] = acc[i];
+    }
+    __syncwarp();
+
+    bool base_done = false;
+    // ---- partners ----
+    for (uint32_t j = j0; j < j1; j++) {
+      const uint32_t loc = a.location[idx] + j;
+      bool flip = true;
+      if (M == 2) flip = need_flip(a.path_length, a.signs, idx, loc);
+      uint32_t c16[M][16];
+      uint32_t nd[M], ncn[M];
+#pragma unroll
+      for (int h = 0; h < M; h++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) c16[h][i] = s_base[warp][h][i][lane];
+        // joined half h = upstream half h | partner half hh   (src/methods.h:137-145)
+        const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
+        const uint32_t o = s.off1[(size_t)loc * M + hh], len = s.off1[(size_t)loc * M + hh + 1] - o;
+        const uint64_t* p0h = p0row + h * Wp;
+        nd[h] = 0;
+        ncn[h] = 0;
+        for (uint32_t i0 = 0; i0 < len; i0 += 32) {
+          const uint32_t i = i0 + lane;
+          const bool valid = i < len;
+          const uint32_t c = valid ? s.car1[o + i] : 0u;
+          const uint64_t w0 = valid ? __ldg(p0h + (c >> 6)) : 0ull;
+          const bool keep = valid && !((w0 >> (c & 63)) & 1ull);
+          const unsigned km = __ballot_sync(0xffffffffu, keep);
+          nd[h] += __popc(km);
+          ncn[h] += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
+          add_masked(c16[h], km, c);
+        }
+        if (inbatch > 0) {
+          flush_planes(c16[h], pl, bits_for(inbatch));
+          inbatch = 0;
+        }
+      }
+
+      bool empty = nd[0] == 0;
+      if (M == 2) empty = empty && nd[M - 1] == 0;
+      if (!empty || !base_done) {
+        if (empty) base_done = true;
+        if (M == 1) {
+          const unsigned total = t0[0] + nd[0];
+          const float* row = a.diagF + diag_base(total);
+#pragma unroll
+          for (int b = 0; b < 32; b++) {
+            const uint32_t v = c16[0][GCRE_C16_REG(b)];
+            const uint32_t c = GCRE_C16_HI(b) ? (v >> 16) : (v & 0xffffu);
+            best[b] = fmaxf(best[b], __ldg(row + c));
+          }
+        } else {
+          const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
+          const double* rowp = a.diagDM + diag_base(tp);
+          const double* rown = a.diagDM + diag_base(tn) + tn;
+#pragma unroll
+          for (int b = 0; b < 32; b++) {
+            const uint32_t vp = c16[0][GCRE_C16_REG(b)], vn = c16[M - 1][GCRE_C16_REG(b)];
+            const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
+            const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
+            // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
+            const double v = __ldg(rowp + cp) + __ldg(rown - cn);
+            best[b] = fmaxf(best[b], __double2float_rn(v));
+          }
+        }
+      }
+
+      if (first_pb) {
+        // ---- kept joined row (src/join_base.cpp:246-249) ----
+        if (KEEP) {
+          const uint64_t* p1row = a.p1 + (size_t)loc * row_words;
+          uint64_t* out = a.pres + (size_t)(a.res_idx[idx] + j) * row_words;
+          for (int k = lane; k < Wp; k += 32) {
+            if (M == 1) {
+              out[k] = p0row[k] | p1row[k];
+            } else {
+              out[k] = p0row[k] | p1row[(flip ? 0 : Wp) + k];
+              out[Wp + k] = p0row[Wp + k] | p1row[(flip ? Wp : 0) + k];
+            }
+          }
+        }
+        // ---- true score -> top-K candidate (src/methods.h:90-94, 253-264) ----
+        if (lane == 0) {
+          double score;
+          int cases, ctrls;
+          unsigned tmax;
+          if (M == 1) {
+            cases = (int)(nc0[0] + ncn[0]);
+            tmax = t0[0] + nd[0];
+            ctrls = (int)tmax - cases;
+            score = a.diagD[diag_base(tmax) + cases];
+          } else {
+            const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
+            const unsigned case_pos = nc0[0] + ncn[0], ctrl_neg = tp - case_pos;
+            const unsigned ctrl_pos = nc0[M - 1] + ncn[M - 1], case_neg = tn - ctrl_pos;
+            score = a.diagD[diag_base(tp) + case_pos] + a.diagD[diag_base(tn) + case_neg];
+            cases = (int)(case_pos + case_neg);
+            ctrls = (int)(ctrl_pos + ctrl_neg);
+            tmax = max(tp, tn);
+          }
+          if (KEEP) atomicMax(a.max_total, tmax);
+          if (score == score) {
+            const unsigned long long key = score_key(score);
+            if (key > a.thr_key) {
+              const unsigned slot = atomicAdd(a.cand_count, 1u);
+              if (slot < a.cand_cap) {
+                Cand cd;
+                cd.key = key; cd.idx = idx; cd.loc = loc; cd.cases = cases; cd.ctrls = ctrls;
+                a.cand[slot] = cd;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (pb_cur >= 0) flush_best(pb_cur);
+}
+
+static inline bool sparse_supported(int n, long long t_needed, int iters) {
+  // u16 carrier indices and u16 packed counters; lanes map to permutation words, so few permutations waste lanes
+  return n <= 65536 && t_needed <= 65535 && iters > 256;
+}
+
+static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count) {
+  const unsigned long long n_work = sp.n_units * (unsigned long long)sp.n_perm_blocks;
+  if (n_work == 0) return cudaSuccess;
+  const unsigned long long want = (n_work + sparse::WARPS - 1) / sparse::WARPS;
+  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * 2);
+  if (M == 1) {
+    if (keep) join_sparse_kernel<1, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+    else join_sparse_kernel<1, false><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+  } else {
+    if (keep) join_sparse_kernel<2, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+    else join_sparse_kernel<2, false><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+  }
+  return cudaGetLastError();
+}
 
 }  // namespace gcre

@@ -66,6 +66,7 @@ def test_schedule_matches_oracle(engine, oracles, method, shape, kernel):
         assert np.array_equal(kept[k], kept_want[k]), f"kept {k} differs"
     for lvl in want:
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} {shape} L{lvl}")
+        assert got[lvl].info["kernel"] == kernel, "the requested kernel family must be the one that ran"
 
 
 @pytest.mark.parametrize("method", ["method1", "method2"])
