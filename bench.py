@@ -83,42 +83,49 @@ def pairs_per_step(w, path_length):
 # clocks
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled through NVML INSIDE the timed region (one sample after every timed step).
+
+    NVML is initialised before the warm-up steps.  (An `nvidia-smi -lms 100` child process, and also a background NVML
+    polling thread, were measured to stretch this process's CUDA API calls by 2-10x on the shared hosts - the step is
+    made of many short launches - so the samples are taken inline, ~0.1 ms each.)"""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.sm, self.reasons, self.smax, self.err, self.nv = device, [], set(), None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def sample(self):
+        nv = self.nv
+        if nv is None:
+            return
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:  # noqa: BLE001
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for name, bit in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.th.join(timeout=2)
-        sm, smax, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                smax = float(r[2])
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax, "samples": len(self.sm),
+                "reasons": sorted(self.reasons), "how": "NVML, one sample after every timed step (inside the timed region)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -162,11 +169,18 @@ def cpu_reference_sample(w, a, target_s, methods=("method1", "method2"), repeats
             ex.join(uids, sub, p1, ex.createPathSet(0))
             return time.time() - t, int(csum[x - 1])
 
-        x = max(64, lv4.n_uids // 200)
-        t_cal, pairs_cal = run(x)
-        rate = pairs_cal / max(t_cal, 1e-6)
-        want_pairs = rate * target_s
-        x2 = int(np.searchsorted(csum, want_pairs)) + 1
+        # two-point calibration (a join call has a fixed cost: per-thread state, for method 2 a per-thread clone of the
+        # (n+1)^2 table, src/methods.h:128), then either the whole level-4 join or a sample sized for ~target_s
+        x1 = max(64, lv4.n_uids // 400)
+        t1, q1 = run(x1)
+        t2, q2 = run(min(lv4.n_uids, 4 * x1))
+        rate = max(q2 - q1, 1) / max(t2 - t1, 1e-6)
+        t_fixed = max(t1 - q1 / rate, 0.0)
+        est_full = t_fixed + lv4.n_pairs / rate
+        if est_full <= 3.0 * target_s:
+            x2 = lv4.n_uids
+        else:
+            x2 = int(np.searchsorted(csum, max(target_s - t_fixed, 0.25 * target_s) * rate)) + 1
         best = None
         for _ in range(repeats):
             t_run, pairs_run = run(x2)
@@ -174,7 +188,8 @@ def cpu_reference_sample(w, a, target_s, methods=("method1", "method2"), repeats
                 best = (t_run, pairs_run)
         total_pp += best[1] * w.n_perms
         total_t += best[0]
-        detail[method] = {"pairs": best[1], "seconds": round(best[0], 3), "pair_perm_per_s": best[1] * w.n_perms / best[0], "setup_levels_1_3_s": round(t_setup, 2)}
+        detail[method] = {"pairs": best[1], "of_level4_pairs": lv4.n_pairs, "seconds": round(best[0], 3), "pair_perm_per_s": best[1] * w.n_perms / best[0],
+                          "fixed_s_per_join": round(t_fixed, 3), "setup_levels_1_3_s": round(t_setup, 2)}
         del ex
     value = total_pp / total_t
     compiler = ""
@@ -183,7 +198,7 @@ def cpu_reference_sample(w, a, target_s, methods=("method1", "method2"), repeats
     except OSError:
         pass
     return {"value": value, "unit": "pair*perm/s", "cores": cores, "kind": kind,
-            "sample": f"level-4 join (paths3 x paths2) over the first upstream rows sized for ~{target_s:.0f} s per method, methods {'+'.join(methods)}, "
+            "sample": f"level-4 join (paths3 x paths2), whole join when it fits ~{3 * target_s:.0f} s else the first upstream rows sized for ~{target_s:.0f} s, per method, methods {'+'.join(methods)}, "
                       f"{w.n_perms} perms, W64={(w.n_patients + 63) // 64}; reference built with {compiler} -O3 -march={po.ref_variant()} -mpopcnt; "
                       f"nthreads={cores}", "detail": detail}
 
@@ -215,17 +230,6 @@ def run_reference_arm(a):
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
-def shard_bounds(count, n_shards):
-    """Contiguous upstream-row ranges balanced by pair count (prefix sums of uid.count)."""
-    csum = np.cumsum(count.astype(np.int64))
-    total = int(csum[-1]) if csum.size else 0
-    cuts = [0]
-    for s in range(1, n_shards):
-        cuts.append(int(np.searchsorted(csum, total * s / n_shards)))
-    cuts.append(count.shape[0])
-    return [(cuts[i], max(cuts[i + 1], cuts[i])) for i in range(n_shards)]
-
-
 def main():
     a = parse_args()
     if a.impl == "reference":
@@ -235,6 +239,7 @@ def main():
     import torch.distributed as dist
 
     from geneticscre_b200 import _lib, api, build, synth
+    from geneticscre_b200 import dist as gdist
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,7 +257,7 @@ def main():
     n = w.n_patients
     names = ["1a", "1b", "2", "3", "4", "5"][: a.path_length + 1]
     last = names[-1]
-    shards = shard_bounds(lv[last].count, world)
+    shards = gdist.shard_bounds(lv[last].count, world)
     my_shard = shards[rank]
     stream = torch.cuda.current_stream()
 
@@ -299,12 +304,9 @@ def main():
             res_set = ex.createPathSet(lv[k].n_pairs) if (keep or (k in ("2", "3") and a.path_length > int(k))) else zero
             if k == last and world > 1:
                 r = ex.join(uid[k], prev, operand, zero, uid_range=my_shard, skip_host_perm=True)
-                lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations)
-                dist.all_reduce(st["perm_t"], op=dist.ReduceOp.MAX)  # ONE collective per join: NCCL allreduce(max)
-                gathered = [None] * world
-                dist.all_gather_object(gathered, [(s.score, s.src, s.trg, s.cases, s.ctrls) for s in r.scores])
-                r.scores = api.merge_topk([[api.Score(*t) for t in g] for g in gathered], a.top_k)
-                r.permuted_scores = st["perm_t"][: w.n_perms].double().cpu().numpy()
+                _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations))
+                # ONE data-path collective per join: NCCL allreduce(max) of the f32 maxima (+ a K-entry gather)
+                gdist.merge_shard_result(r, a.top_k, api.merge_topk, api.Score, dist, device_perm=st["perm_t"], n_perms=w.n_perms)
             else:
                 r = ex.join(uid[k], prev, operand, res_set)
             info[k] = r.info
@@ -331,23 +333,38 @@ def main():
             torch.cuda.synchronize()
 
     # ---- warm-up + timed region (CUDA events on the stream the engine launches on) ----
-    for _ in range(a.warmup):
-        step_resident()
-    sync_all()
+    dbg = bool(os.environ.get("GCRE_BENCH_DEBUG"))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(a.warmup):
+        t_dbg = time.perf_counter()
+        step_resident()
+        if dbg:
+            torch.cuda.synchronize()
+            sys.stderr.write(f"[bench] warmup step {i}: {(time.perf_counter() - t_dbg) * 1e3:.1f} ms\n")
+    sync_all()
+    import gc
+
+    gc.collect()
+    gc.freeze()   # keep the interpreter's cyclic GC (hundreds of ms with torch imported) out of the timed region
+    gc.disable()
     l0 = launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     last_out = None
-    for _ in range(a.steps):
+    for i in range(a.steps):
+        t_dbg = time.perf_counter()
         last_out = step_resident()
+        sampler.sample()
+        if dbg:
+            sys.stderr.write(f"[bench] timed step {i}: {(time.perf_counter() - t_dbg) * 1e3:.1f} ms (host clock, no sync)\n")
     ev1.record(stream)
     sync_all()
     ms_total = ev0.elapsed_time(ev1)
     n_launch = launches() - l0
     clocks = sampler.stop() if rank == 0 else None
+    gc.enable()
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)

@@ -7,8 +7,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -77,6 +79,46 @@ struct DevBuf {  // grow-only device scratch
   }
 };
 
+// Size-keyed cache of device blocks for path sets and carrier-list views.  The level schedule allocates and frees the
+// same (large) sizes over and over; going to the driver each time costs milliseconds and, with the stream-ordered pool,
+// was measured to stall for 100s of ms when the pool had to grow or remap.  Blocks are only reused by work of the same
+// exec, which is serialised on one stream, so reuse needs no extra synchronisation.
+struct BlockCache {
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached_bytes = 0;
+  static size_t round_up(size_t b) { return (std::max<size_t>(b, 1) + 511) & ~(size_t)511; }
+  cudaError_t alloc(void** out, size_t bytes) {
+    const size_t want = round_up(bytes);
+    auto it = free_blocks.lower_bound(want);
+    if (it != free_blocks.end() && it->first <= want + want / 8) {  // at most 12.5 % slack
+      *out = it->second;
+      cached_bytes -= it->first;
+      free_blocks.erase(it);
+      return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e == cudaErrorMemoryAllocation && !free_blocks.empty()) {
+      cudaGetLastError();
+      release_all();
+      e = cudaMalloc(out, want);
+    }
+    return e;
+  }
+  // size actually backing a block handed out for `bytes` is not tracked per pointer: callers pass the same `bytes`
+  // they allocated with, and a reused (slightly larger) block is re-filed under the requested size's rounded value;
+  // the slack stays attached to the pointer and is returned to the driver when the cache is released.
+  void free(void* p, size_t bytes) {
+    if (!p) return;
+    free_blocks.emplace(round_up(bytes), p);
+    cached_bytes += round_up(bytes);
+  }
+  void release_all() {
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+
 struct gcre_exec {
   int M = 1, n_cases = 0, n_ctrls = 0, n = 0, W64 = 0, Wp = 0, iters = 0, Ip = 0, Iw = 0, device = 0, sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -96,6 +138,7 @@ struct gcre_exec {
   // outputs / scratch
   int* d_perm_max = nullptr;
   unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total, [2..3] 64-bit work counter of the sparse kernel
+  mutable BlockCache blocks;
   DevBuf cand, uid_count, uid_loc, uid_prefix, uid_res, uid_units, signs, scratch, scan_tmp;
   unsigned* h_scalars = nullptr;  // pinned
 };
@@ -109,10 +152,11 @@ struct gcre_pathset {
 };
 
 static void drop_view(gcre_pathset* ps) {
-  cudaStream_t st = ps->ex->stream;
-  if (ps->view.off) cudaFreeAsync(ps->view.off, st);
-  if (ps->view.car) cudaFreeAsync(ps->view.car, st);
-  if (ps->view.ncase) cudaFreeAsync(ps->view.ncase, st);
+  BlockCache& bc = ps->ex->blocks;
+  const size_t items = (size_t)ps->size * ps->ex->M;
+  bc.free(ps->view.off, (items + 1) * 4);
+  bc.free(ps->view.ncase, std::max<size_t>(items, 1) * 4);
+  bc.free(ps->view.car, std::max<size_t>(ps->view.total, 1) * 2);
   ps->view = SparseView();
 }
 
@@ -166,13 +210,6 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
   int rc = [&]() -> int {
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&ex->sm_count, cudaDevAttrMultiProcessorCount, device));
-    {
-      // stream-ordered allocations (path sets, carrier-list views) come from the device pool and stay cached in it
-      cudaMemPool_t pool;
-      CK(cudaDeviceGetDefaultMemPool(&pool, device));
-      unsigned long long keep_all = ~0ull;
-      CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
-    }
     CK(cudaStreamCreateWithFlags(&ex->own_stream, cudaStreamNonBlocking));
     ex->stream = ex->own_stream;
     CK(cudaEventCreate(&ex->ev0));
@@ -211,6 +248,7 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   cudaFree(ex->d_perm_max);
   cudaFree(ex->d_scalars);
   if (ex->h_scalars) cudaFreeHost(ex->h_scalars);
+  ex->blocks.release_all();
   ex->cand.release();
   ex->uid_count.release();
   ex->uid_loc.release();
@@ -354,14 +392,14 @@ extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_path
   ps->size = size;
   const size_t bytes = (size_t)size * row_words(ex) * 8;
   if (bytes) {
-    cudaError_t e = cudaMallocAsync(&ps->d_rows, bytes, ex->stream);
+    cudaError_t e = ex->blocks.alloc((void**)&ps->d_rows, bytes);
     if (e != cudaSuccess) {
       delete ps;
-      return fail(GCRE_ERR_NOMEM, "cudaMallocAsync of %zu bytes for a path set failed: %s", bytes, cudaGetErrorString(e));
+      return fail(GCRE_ERR_NOMEM, "device allocation of %zu bytes for a path set failed: %s", bytes, cudaGetErrorString(e));
     }
     e = cudaMemsetAsync(ps->d_rows, 0, bytes, ex->stream);
     if (e != cudaSuccess) {
-      cudaFreeAsync(ps->d_rows, ex->stream);
+      ex->blocks.free(ps->d_rows, bytes);
       delete ps;
       return fail(GCRE_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
@@ -373,7 +411,7 @@ extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_path
 extern "C" int gcre_pathset_destroy(gcre_pathset* ps) {
   if (!ps) return GCRE_OK;
   cudaSetDevice(ps->ex->device);
-  if (ps->d_rows) cudaFreeAsync(ps->d_rows, ps->ex->stream);  // stream-ordered: no host synchronisation
+  ps->ex->blocks.free(ps->d_rows, (size_t)ps->size * row_words(ps->ex) * 8);  // back to the exec's block cache, no driver call
   drop_view(ps);
   delete ps;
   return GCRE_OK;
@@ -619,8 +657,8 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
   if (ps->view.valid) return GCRE_OK;
   drop_view(ps);
   const long long items = (long long)ps->size * ex->M;
-  CK(cudaMallocAsync(&ps->view.off, (size_t)(items + 1) * 4, ex->stream));
-  CK(cudaMallocAsync(&ps->view.ncase, std::max<size_t>(items, 1) * 4, ex->stream));
+  CK(ex->blocks.alloc((void**)&ps->view.off, (size_t)(items + 1) * 4));
+  CK(ex->blocks.alloc((void**)&ps->view.ncase, std::max<size_t>(items, 1) * 4));
   CK(cudaMemsetAsync(ps->view.off, 0, (size_t)(items + 1) * 4, ex->stream));
   uint32_t total = 0;
   if (items > 0) {
@@ -639,7 +677,8 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
     CK(cudaMemcpyAsync(&total, ps->view.off + items, 4, cudaMemcpyDeviceToHost, ex->stream));
     CK(cudaStreamSynchronize(ex->stream));
   }
-  CK(cudaMallocAsync(&ps->view.car, std::max<size_t>(total, 1) * 2, ex->stream));
+  ps->view.total = total;
+  CK(ex->blocks.alloc((void**)&ps->view.car, std::max<size_t>(total, 1) * 2));
   if (items > 0) {
     build_lists_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ps->view.off, ps->view.car, ps->view.ncase);
     CK(cudaGetLastError());
@@ -804,16 +843,38 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   const bool sparse_k = kernel == GCRE_KERNEL_SPARSE;
   const unsigned long long per_item = sparse_k ? sparse::PB : 1;
   const unsigned long long item_lo = sparse_k ? h_units[ub] : pair_lo, item_hi = sparse_k ? h_units[ue] : pair_hi;
-  const unsigned long long chunk_max = (4ull << 20) / per_item;
-  unsigned long long chunk = (64ull << 10) / per_item;
+  // Launch plan.  Top-K candidates are appended by the kernels only when their score beats the K-th best known so far,
+  // and a launch must be able to hold every candidate it may produce:
+  //   * small joins: one launch with room for every pair;
+  //   * large joins: a short prefix (threshold unknown: every pair is a candidate) establishes the K-th score, then
+  //     ONE launch covers the rest with a fixed candidate budget.  Pairs are visited in ascending (src, trg) order
+  //     across launches, so later pairs only displace on a strictly greater score.  If the budget overflows (scores that
+  //     keep rising), that launch's candidates are dropped and the range is redone in safe chunks (cap = chunk size);
+  //     permutation maxima are max-merged, so re-scoring a pair is harmless.
+  struct Seg { unsigned long long b, e; bool safe; };
+  std::vector<Seg> plan;
+  // GCRE_TEST_SMALL_PLAN=1 (test hook) shrinks every size so the prefix / budget-overflow / redo paths run on tiny joins
+  const bool tiny_plan = std::getenv("GCRE_TEST_SMALL_PLAN") != nullptr;
+  const unsigned long long small_items = std::max<unsigned long long>(1, (tiny_plan ? 128ull : (2ull << 20)) / per_item);
+  const unsigned long long prefix_items = std::max<unsigned long long>(1, (tiny_plan ? 64ull : (64ull << 10)) / per_item);
+  const unsigned budget = tiny_plan ? 16u : (1u << 20);
+  const unsigned long long redo_first = std::max<unsigned long long>(1, (tiny_plan ? 128ull : (256ull << 10)) / per_item);
+  const unsigned long long redo_max = std::max<unsigned long long>(1, (tiny_plan ? 512ull : (4ull << 20)) / per_item);
+  if (item_hi - item_lo <= small_items) {
+    if (item_hi > item_lo) plan.push_back({item_lo, item_hi, true});
+  } else {
+    plan.push_back({item_lo, item_lo + prefix_items, true});
+    plan.push_back({item_lo + prefix_items, item_hi, false});
+  }
   std::vector<gcre_score> held;
   std::vector<Cand> h_cand;
   unsigned long long thr_key = score_key(-std::numeric_limits<double>::infinity());
   double kernel_ms = 0.0;
   int launches = 0;
-  for (unsigned long long p = item_lo; p < item_hi;) {
-    const unsigned long long pe = std::min(item_hi, p + chunk);
-    const unsigned cap = (unsigned)((pe - p) * per_item);
+  for (size_t si = 0; si < plan.size(); si++) {
+    const Seg seg = plan[si];
+    const unsigned long long p = seg.b, pe = seg.e;
+    const unsigned cap = seg.safe ? (unsigned)((pe - p) * per_item) : budget;
     CKS(ex->cand.ensure((size_t)cap * sizeof(Cand)));
     jp.cand = (Cand*)ex->cand.p;
     jp.cand_cap = cap;
@@ -838,7 +899,20 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ex->ev0, ex->ev1));
     kernel_ms += ms;
-    const unsigned n_cand = std::min(ex->h_scalars[0], cap);
+    if (ex->h_scalars[0] > cap) {
+      // budget overflow: redo this range in safe chunks (growing x8 up to 4M pairs)
+      unsigned long long chunk = redo_first;
+      std::vector<Seg> redo;
+      for (unsigned long long q = p; q < pe;) {
+        const unsigned long long qe = std::min(pe, q + chunk);
+        redo.push_back({q, qe, true});
+        q = qe;
+        chunk = std::min(chunk * 8, redo_max);
+      }
+      plan.insert(plan.begin() + si + 1, redo.begin(), redo.end());
+      continue;
+    }
+    const unsigned n_cand = ex->h_scalars[0];
     if (n_cand) {
       h_cand.resize(n_cand);
       CK(cudaMemcpyAsync(h_cand.data(), ex->cand.p, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, ex->stream));
@@ -856,12 +930,10 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
       if ((int)held.size() == top_k) {
         double kth = held[0].score;
         for (const auto& sc : held) kth = std::min(kth, sc.score);
-        // later chunks hold larger (src, trg) only, so a tie with the K-th score can no longer win a place
+        // later launches hold larger (src, trg) only, so a tie with the K-th score can no longer win a place
         thr_key = score_key(kth);
       }
     }
-    p = pe;
-    chunk = std::min(chunk * 8, chunk_max);
   }
   if (keep) {
     paths_res->max_half_pop = (pair_lo == 0 && pair_hi == total) ? (long long)ex->h_scalars[1] : -1;

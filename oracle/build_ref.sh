@@ -27,3 +27,11 @@ g++ -std=c++11 -O3 -march=x86-64-v2 -mpopcnt -pthread -w -I"$OUT/stub" -I"$REF/s
     "$REF/test/harness.cpp" "$REF/test/test.cpp" "$REF/src/join_base.cpp" -o "$OUT/ref_harness"
 g++ --version | head -1 > "$OUT/COMPILER.txt"
 echo "[build_ref] built: $(ls $OUT | tr '\n' ' ')"
+# Drop-in proof: the reference's replay harness, UNMODIFIED, compiled against OUR headers (include/gcre/) and linked to
+# the CUDA engine instead of the reference's join_base.cpp.  Needs geneticscre_b200/libgcre_b200.so (build it first).
+ROOT="$(dirname "$HERE")"
+if [ -f "$ROOT/geneticscre_b200/libgcre_b200.so" ]; then
+  g++ -std=c++11 -O2 -pthread -w -I"$ROOT/include/gcre" -I"$REF/test" "$REF/test/harness.cpp" "$REF/test/test.cpp" \
+      -L"$ROOT/geneticscre_b200" -lgcre_b200 -Wl,-rpath,'$ORIGIN/../../geneticscre_b200' -o "$OUT/b200_harness" \
+    && echo "[build_ref] built b200_harness (reference test/harness.cpp on the B200 engine)"
+fi
