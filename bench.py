@@ -36,7 +36,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(n_cases=5000, n_ctrls=5000, n_genes=15000, n_edges=60000, n_perms=1000, path_length=4, top_k=10, seed=20261021)
+WORKLOAD = dict(n_cases=5000, n_ctrls=5000, n_genes=15000, n_edges=150000, n_perms=1000, path_length=4, top_k=10, seed=20261021)
 
 
 def parse_args():
@@ -131,93 +131,100 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU reference arm
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(w, a, target_s, methods=("method1", "method2"), repeats=1):
-    """Times the reference's own JoinExec::join (oracle/_ref) on all host cores over a bounded sample of the level-4
-    join: the first X upstream rows (same W, same permutation count, same value table)."""
-    from geneticscre_b200 import schedule
-    from oracle import pyoracle as po
+class ReferenceArm:
+    """The reference's own JoinExec::join (oracle/_ref: unmodified reference sources, g++ -O3 -march=<host level> -mpopcnt)
+    on all host cores.  setup() replays levels 1-3 once per method (untimed, like our arm's resident inputs); sample()
+    times the last-level join - the whole join when it fits the time budget, else a bounded prefix of upstream rows."""
 
-    cores = os.cpu_count() or 1
-    kind = "reference" if po.ref_available() else "port"
-    lv4 = w.net.levels["4"] if a.path_length >= 4 else w.net.levels[str(a.path_length)]
-    last = "4" if a.path_length >= 4 else str(a.path_length)
-    total_pp, total_t, detail = 0.0, 0.0, {}
-    for method in methods:
-        if kind == "reference":
-            ex = po.RefExec(method, w.n_cases, w.n_ctrls, w.n_perms)
-            ex.nthreads = cores
-        else:
-            ex = po.OracleExec(method, w.n_cases, w.n_ctrls, w.n_perms)
-            cores = 1
-        ex.top_k = a.top_k
-        ex.setValueTable(w.value_table)
-        ex.setPermutedMasks(w.perm_masks)
-        t0 = time.time()
-        _, kept = schedule.replay_levels(ex, po.UidRelSet, w, a.path_length - 1 if last == "4" else a.path_length, only=())
-        t_setup = time.time() - t0
-        # calibrate: time a small slice, then size the sample for ~target_s
-        p0_all, p1 = (kept["paths3"], kept["paths2"]) if last == "4" else (None, None)
-        if p0_all is None:
-            raise RuntimeError("cpu baseline needs path_length >= 4")
-        csum = np.cumsum(lv4.count.astype(np.int64))
+    def __init__(self, w, a, methods=("method1", "method2")):
+        from geneticscre_b200 import schedule
+        from oracle import pyoracle as po
 
-        def run(x):
-            x = int(min(max(x, 1), lv4.n_uids))
-            uids = po.UidRelSet(4, lv4.src[:x], lv4.trg[:x], lv4.count[:x], lv4.location[:x], lv4.signs[:x])
-            sub = p0_all.select(np.arange(x, dtype=np.int32))
-            t = time.time()
-            ex.join(uids, sub, p1, ex.createPathSet(0))
-            return time.time() - t, int(csum[x - 1])
+        if a.path_length < 4:
+            raise RuntimeError("the CPU baseline times the level-4 join: needs path_length >= 4")
+        self.po, self.w, self.a, self.methods = po, w, a, methods
+        self.kind = "reference" if po.ref_available() else "port"
+        self.cores = (os.cpu_count() or 1) if self.kind == "reference" else 1
+        self.lv = w.net.levels["4"]
+        self.csum = np.cumsum(self.lv.count.astype(np.int64))
+        self.state = {}
+        for method in methods:
+            if self.kind == "reference":
+                ex = po.RefExec(method, w.n_cases, w.n_ctrls, w.n_perms)
+                ex.nthreads = self.cores
+            else:
+                ex = po.OracleExec(method, w.n_cases, w.n_ctrls, w.n_perms)
+            ex.top_k = a.top_k
+            ex.setValueTable(w.value_table)
+            ex.setPermutedMasks(w.perm_masks)
+            t0 = time.time()
+            _, kept = schedule.replay_levels(ex, po.UidRelSet, w, 3, only=())
+            self.state[method] = dict(ex=ex, p0=kept["paths3"], p1=kept["paths2"], setup_s=time.time() - t0, plan=None)
 
-        # two-point calibration (a join call has a fixed cost: per-thread state, for method 2 a per-thread clone of the
-        # (n+1)^2 table, src/methods.h:128), then either the whole level-4 join or a sample sized for ~target_s
-        x1 = max(64, lv4.n_uids // 400)
-        t1, q1 = run(x1)
-        t2, q2 = run(min(lv4.n_uids, 4 * x1))
-        rate = max(q2 - q1, 1) / max(t2 - t1, 1e-6)
-        t_fixed = max(t1 - q1 / rate, 0.0)
-        est_full = t_fixed + lv4.n_pairs / rate
-        if est_full <= 3.0 * target_s:
-            x2 = lv4.n_uids
-        else:
-            x2 = int(np.searchsorted(csum, max(target_s - t_fixed, 0.25 * target_s) * rate)) + 1
-        best = None
-        for _ in range(repeats):
-            t_run, pairs_run = run(x2)
-            if best is None or pairs_run / t_run > best[1] / best[0]:
-                best = (t_run, pairs_run)
-        total_pp += best[1] * w.n_perms
-        total_t += best[0]
-        detail[method] = {"pairs": best[1], "of_level4_pairs": lv4.n_pairs, "seconds": round(best[0], 3), "pair_perm_per_s": best[1] * w.n_perms / best[0],
-                          "fixed_s_per_join": round(t_fixed, 3), "setup_levels_1_3_s": round(t_setup, 2)}
-        del ex
-    value = total_pp / total_t
-    compiler = ""
-    try:
-        compiler = open(os.path.join(ROOT, "oracle", "_ref", "COMPILER.txt")).read().strip()
-    except OSError:
-        pass
-    return {"value": value, "unit": "pair*perm/s", "cores": cores, "kind": kind,
-            "sample": f"level-4 join (paths3 x paths2), whole join when it fits ~{3 * target_s:.0f} s else the first upstream rows sized for ~{target_s:.0f} s, per method, methods {'+'.join(methods)}, "
-                      f"{w.n_perms} perms, W64={(w.n_patients + 63) // 64}; reference built with {compiler} -O3 -march={po.ref_variant()} -mpopcnt; "
-                      f"nthreads={cores}", "detail": detail}
+    def _run(self, st, x):
+        lv, po = self.lv, self.po
+        x = int(min(max(x, 1), lv.n_uids))
+        uids = po.UidRelSet(4, lv.src[:x], lv.trg[:x], lv.count[:x], lv.location[:x], lv.signs[:x])
+        sub = st["p0"] if x == lv.n_uids else st["p0"].select(np.arange(x, dtype=np.int32))
+        t = time.time()
+        st["ex"].join(uids, sub, st["p1"], st["ex"].createPathSet(0))
+        return time.time() - t, int(self.csum[x - 1])
+
+    def sample(self, target_s):
+        """One bounded sample per method; returns the cpu_baseline object."""
+        lv, w = self.lv, self.w
+        total_pp, total_t, detail = 0.0, 0.0, {}
+        for method in self.methods:
+            st = self.state[method]
+            if st["plan"] is None:
+                # two-point calibration: a join call has a fixed cost (per-thread state; for method 2 a per-thread clone
+                # of the (n+1)^2 table, src/methods.h:128) plus a per-pair cost
+                x1 = max(64, lv.n_uids // 400)
+                t1, q1 = self._run(st, x1)
+                t2, q2 = self._run(st, min(lv.n_uids, 4 * x1))
+                rate = max(q2 - q1, 1) / max(t2 - t1, 1e-6)
+                t_fixed = max(t1 - q1 / rate, 0.0)
+                if t_fixed + lv.n_pairs / rate <= 3.0 * target_s:
+                    x = lv.n_uids
+                else:
+                    x = int(np.searchsorted(self.csum, max(target_s - t_fixed, 0.25 * target_s) * rate)) + 1
+                st["plan"] = (x, t_fixed)
+            x, t_fixed = st["plan"]
+            t_run, pairs_run = self._run(st, x)
+            total_pp += pairs_run * w.n_perms
+            total_t += t_run
+            detail[method] = {"pairs": pairs_run, "of_level4_pairs": lv.n_pairs, "seconds": round(t_run, 3),
+                              "pair_perm_per_s": pairs_run * w.n_perms / t_run, "fixed_s_per_join": round(t_fixed, 3),
+                              "setup_levels_1_3_s": round(st["setup_s"], 2)}
+        compiler = ""
+        try:
+            compiler = open(os.path.join(ROOT, "oracle", "_ref", "COMPILER.txt")).read().strip()
+        except OSError:
+            pass
+        how = (f"reference built with {compiler} -O3 -march={self.po.ref_variant()} -mpopcnt" if self.kind == "reference"
+               else "scalar C restatement (oracle/gcre_oracle.c), the reference build is absent")
+        return {"value": total_pp / total_t, "unit": "pair*perm/s", "cores": self.cores, "kind": self.kind,
+                "sample": f"level-4 join (paths3 x paths2) per method ({'+'.join(self.methods)}): the whole join when it fits ~{3 * target_s:.0f} s, "
+                          f"else the first upstream rows sized for ~{target_s:.0f} s; {w.n_perms} perms, W64={(w.n_patients + 63) // 64}; {how}; "
+                          f"nthreads={self.cores}", "seconds": round(total_t, 3), "detail": detail}
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, _ = make_workload(a)
     t0 = time.time()
+    w, _ = make_workload(a)
+    arm = ReferenceArm(w, a)
+    per_method_s = max(1.0, min(a.cpu_seconds, 90.0 / max(a.steps + a.warmup, 1) / 2))
     vals = []
-    per_step = max(2.0, min(a.cpu_seconds, 60.0 / max(a.steps + a.warmup, 1)))
     for i in range(a.warmup + a.steps):
-        r = cpu_reference_sample(w, a, per_step / 2)
+        r = arm.sample(per_method_s)
         if i >= a.warmup:
             vals.append(r)
     value = float(np.mean([v["value"] for v in vals])) if vals else 0.0
-    last = vals[-1] if vals else {"cores": os.cpu_count(), "kind": "reference", "sample": ""}
-    ms = 1e3 * float(np.mean([sum(d["seconds"] for d in v["detail"].values()) for v in vals])) if vals else None
+    last = vals[-1] if vals else {"cores": arm.cores, "kind": arm.kind, "sample": ""}
+    ms = 1e3 * float(np.mean([v["seconds"] for v in vals])) if vals else None
     line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitsets, u32 counts, f64 scores",
             "data": "synthetic", "impl": "reference", "config": workload_config(a, w),
@@ -451,7 +458,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
-            cpu = cpu_reference_sample(w, a, a.cpu_seconds)
+            cpu = ReferenceArm(w, a).sample(a.cpu_seconds)
         except Exception as e:  # the GPU numbers stand on their own
             cpu = {"value": None, "unit": "pair*perm/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}
 

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -11,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <unordered_map>
 #include <new>
 #include <string>
 #include <vector>
@@ -51,6 +53,25 @@ static int fail(int code, const char* fmt, ...) {
     if (s__ != GCRE_OK) return s__; \
   } while (0)
 
+// GCRE_TRACE=1: host-side phase timings of every join on stderr (development aid)
+struct PhaseTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  std::string line;
+  PhaseTrace() : on(std::getenv("GCRE_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* name) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[64];
+    snprintf(buf, sizeof buf, " %s=%.3f", name, std::chrono::duration<double, std::milli>(now - t).count());
+    line += buf;
+    t = now;
+  }
+  void done(const char* what) {
+    if (on) fprintf(stderr, "[gcre trace] %s:%s\n", what, line.c_str());
+  }
+};
+
 static std::atomic<unsigned long long> g_launches{0};
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
@@ -84,15 +105,14 @@ struct DevBuf {  // grow-only device scratch
 // was measured to stall for 100s of ms when the pool had to grow or remap.  Blocks are only reused by work of the same
 // exec, which is serialised on one stream, so reuse needs no extra synchronisation.
 struct BlockCache {
-  std::multimap<size_t, void*> free_blocks;
-  size_t cached_bytes = 0;
+  std::multimap<size_t, void*> free_blocks;     // capacity -> block
+  std::unordered_map<void*, size_t> capacity;   // every block this cache ever handed out or holds
   static size_t round_up(size_t b) { return (std::max<size_t>(b, 1) + 511) & ~(size_t)511; }
   cudaError_t alloc(void** out, size_t bytes) {
     const size_t want = round_up(bytes);
     auto it = free_blocks.lower_bound(want);
     if (it != free_blocks.end() && it->first <= want + want / 8) {  // at most 12.5 % slack
       *out = it->second;
-      cached_bytes -= it->first;
       free_blocks.erase(it);
       return cudaSuccess;
     }
@@ -102,20 +122,24 @@ struct BlockCache {
       release_all();
       e = cudaMalloc(out, want);
     }
+    if (e == cudaSuccess) capacity[*out] = want;
     return e;
   }
-  // size actually backing a block handed out for `bytes` is not tracked per pointer: callers pass the same `bytes`
-  // they allocated with, and a reused (slightly larger) block is re-filed under the requested size's rounded value;
-  // the slack stays attached to the pointer and is returned to the driver when the cache is released.
-  void free(void* p, size_t bytes) {
+  void free(void* p, size_t /*bytes*/) {
     if (!p) return;
-    free_blocks.emplace(round_up(bytes), p);
-    cached_bytes += round_up(bytes);
+    auto it = capacity.find(p);
+    if (it == capacity.end()) {  // not ours (should not happen): hand it back to the driver
+      cudaFree(p);
+      return;
+    }
+    free_blocks.emplace(it->second, p);
   }
   void release_all() {
-    for (auto& kv : free_blocks) cudaFree(kv.second);
+    for (auto& kv : free_blocks) {
+      cudaFree(kv.second);
+      capacity.erase(kv.second);
+    }
     free_blocks.clear();
-    cached_bytes = 0;
   }
 };
 
@@ -141,6 +165,9 @@ struct gcre_exec {
   mutable BlockCache blocks;
   DevBuf cand, uid_count, uid_loc, uid_prefix, uid_res, uid_units, signs, scratch, scan_tmp;
   unsigned* h_scalars = nullptr;  // pinned
+  std::vector<int32_t> h_count;   // host staging of the join index, kept across joins
+  std::vector<uint32_t> h_loc;
+  std::vector<unsigned long long> h_prefix, h_res, h_units;
 };
 
 struct gcre_pathset {
@@ -155,8 +182,9 @@ static void drop_view(gcre_pathset* ps) {
   BlockCache& bc = ps->ex->blocks;
   const size_t items = (size_t)ps->size * ps->ex->M;
   bc.free(ps->view.off, (items + 1) * 4);
+  bc.free(ps->view.len, std::max<size_t>(items, 1) * 4);
   bc.free(ps->view.ncase, std::max<size_t>(items, 1) * 4);
-  bc.free(ps->view.car, std::max<size_t>(ps->view.total, 1) * 2);
+  bc.free(ps->view.car, std::max<size_t>(ps->view.total, 8) * 2);
   ps->view = SparseView();
 }
 
@@ -205,7 +233,7 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
   ex->Wp = (ex->W64 + 1) & ~1;
   ex->iters = iters;
   ex->Ip = ((std::max(iters, 1) + dense::TI - 1) / dense::TI) * dense::TI;
-  ex->Iw = ex->Ip / 32;
+  ex->Iw = ((ex->Ip / 32 + 31) / 32) * 32;  // words per patient row of the patient-major masks: whole 1,024-perm blocks
   ex->device = device;
   int rc = [&]() -> int {
     CK(cudaSetDevice(device));
@@ -318,7 +346,9 @@ static int rebuild_mask_layouts(gcre_exec* ex) {
 
 static int ensure_patient_major(gcre_exec* ex) {
   if (ex->pt_valid) return GCRE_OK;
-  if (!ex->d_pt) CK(cudaMalloc(&ex->d_pt, std::max<size_t>((size_t)ex->n * ex->Iw, 1) * 4));
+  // n + 1 rows: row n is all zero and is what the sentinel entries that pad the carrier lists point at
+  if (!ex->d_pt) CK(cudaMalloc(&ex->d_pt, (size_t)(ex->n + 1) * ex->Iw * 4));
+  CK(cudaMemsetAsync(ex->d_pt + (size_t)ex->n * ex->Iw, 0, (size_t)ex->Iw * 4, ex->stream));
   const long long warps = (long long)ex->Iw * ((ex->n + 31) / 32);
   masks_to_patient_major_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>(ex->d_masks, ex->iters, ex->W64, ex->n, ex->d_pt, ex->Iw);
   CK(cudaGetLastError());
@@ -658,33 +688,34 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
   drop_view(ps);
   const long long items = (long long)ps->size * ex->M;
   CK(ex->blocks.alloc((void**)&ps->view.off, (size_t)(items + 1) * 4));
+  CK(ex->blocks.alloc((void**)&ps->view.len, std::max<size_t>(items, 1) * 4));
   CK(ex->blocks.alloc((void**)&ps->view.ncase, std::max<size_t>(items, 1) * 4));
   CK(cudaMemsetAsync(ps->view.off, 0, (size_t)(items + 1) * 4, ex->stream));
   uint32_t total = 0;
   if (items > 0) {
-    // counts -> exclusive offsets (cub scan over items + 1 entries, the last input is 0)
+    // true counts + padded counts -> exclusive offsets (cub scan over items + 1 entries, the last input is 0)
     CKS(ex->scratch.ensure((size_t)(items + 1) * 4));
-    uint32_t* cnt = (uint32_t*)ex->scratch.p;
-    CK(cudaMemsetAsync(cnt, 0, (size_t)(items + 1) * 4, ex->stream));
-    half_popcount_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, cnt);
+    uint32_t* padded = (uint32_t*)ex->scratch.p;
+    CK(cudaMemsetAsync(padded, 0, (size_t)(items + 1) * 4, ex->stream));
+    half_popcount_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ps->view.len, padded);
     CK(cudaGetLastError());
     LAUNCHED();
     size_t tmp_bytes = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, ps->view.off, (int)(items + 1), ex->stream));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, padded, ps->view.off, (int)(items + 1), ex->stream));
     CKS(ex->scan_tmp.ensure(tmp_bytes));
-    CK(cub::DeviceScan::ExclusiveSum(ex->scan_tmp.p, tmp_bytes, cnt, ps->view.off, (int)(items + 1), ex->stream));
+    CK(cub::DeviceScan::ExclusiveSum(ex->scan_tmp.p, tmp_bytes, padded, ps->view.off, (int)(items + 1), ex->stream));
     LAUNCHED();
     CK(cudaMemcpyAsync(&total, ps->view.off + items, 4, cudaMemcpyDeviceToHost, ex->stream));
     CK(cudaStreamSynchronize(ex->stream));
   }
   ps->view.total = total;
-  CK(ex->blocks.alloc((void**)&ps->view.car, std::max<size_t>(total, 1) * 2));
+  CK(ex->blocks.alloc((void**)&ps->view.car, std::max<size_t>(total, 8) * 2));
   if (items > 0) {
-    build_lists_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ps->view.off, ps->view.car, ps->view.ncase);
+    build_lists_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ex->n, ps->view.off, ps->view.car,
+                                                                         ps->view.ncase);
     CK(cudaGetLastError());
     LAUNCHED();
   }
-  ps->view.total = total;
   ps->view.valid = true;
   return GCRE_OK;
 }
@@ -729,12 +760,17 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   CKS(use_device(ex));
   if (top_k < 1) top_k = 1;
   const bool keep = paths_res && paths_res->size != 0;
+  PhaseTrace tr;
 
   // ---- pre-checks, src/join_base.cpp:196-200 ----
   if (n_uids != paths0->size) return fail(GCRE_ERR_ASSERT, "assertion");
-  std::vector<int32_t> h_count(n_uids);
-  std::vector<uint32_t> h_loc(n_uids);
-  std::vector<unsigned long long> h_prefix((size_t)n_uids + 1), h_res(n_uids);
+  std::vector<int32_t>& h_count = ex->h_count;
+  std::vector<uint32_t>& h_loc = ex->h_loc;
+  std::vector<unsigned long long>&h_prefix = ex->h_prefix, &h_res = ex->h_res;
+  h_count.resize(n_uids);
+  h_loc.resize(n_uids);
+  h_prefix.resize((size_t)n_uids + 1);
+  h_res.resize(n_uids);
   unsigned long long total = 0;
   unsigned long long max_loc_end = 0;
   for (uint32_t u = 0; u < n_uids; u++) {
@@ -766,12 +802,15 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   }
   const unsigned long long pair_lo = h_prefix[ub], pair_hi = h_prefix[ue];
 
+  tr.mark("checks");
   // ---- value-table coverage: a joined half-row has at most maxpop0 + maxpop1 carriers ----
   long long mp0 = 0, mp1 = 0;
   CKS(pathset_max_half_pop(const_cast<gcre_pathset*>(paths0), &mp0));
   CKS(pathset_max_half_pop(const_cast<gcre_pathset*>(paths1), &mp1));
   const long long t_needed = std::min<long long>(ex->n, mp0 + mp1);
+  tr.mark("maxpop");
   CKS(ensure_diag(ex, t_needed));
+  tr.mark("diag");
 
   // ---- kernel choice ----
   int kernel = opts ? opts->kernel : GCRE_KERNEL_AUTO;
@@ -781,7 +820,8 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, 1 << 30)) kernel = GCRE_KERNEL_DENSE;
   SparseParams sp;
   memset(&sp, 0, sizeof sp);
-  std::vector<unsigned long long> h_units;
+  std::vector<unsigned long long>& h_units = ex->h_units;
+  h_units.clear();
   if (kernel == GCRE_KERNEL_SPARSE) {
     CKS(ensure_patient_major(ex));
     CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths0)));
@@ -794,13 +834,15 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
     }
     h_units[n_uids] = nu;
     CKS(upload(ex, ex->uid_units, h_units));
-    sp.off0 = paths0->view.off; sp.car0 = paths0->view.car; sp.ncase0 = paths0->view.ncase;
-    sp.off1 = paths1->view.off; sp.car1 = paths1->view.car; sp.ncase1 = paths1->view.ncase;
+    sp.off0 = paths0->view.off; sp.len0 = paths0->view.len; sp.car0 = paths0->view.car; sp.ncase0 = paths0->view.ncase;
+    sp.off1 = paths1->view.off; sp.len1 = paths1->view.len; sp.car1 = paths1->view.car; sp.ncase1 = paths1->view.ncase;
+    sp.n = ex->n;
     sp.unit_prefix = (const unsigned long long*)ex->uid_units.p;
     sp.work_counter = (unsigned long long*)(ex->d_scalars + 2);
-    sp.n_perm_blocks = (ex->Iw + 31) / 32;
+    sp.n_perm_blocks = ex->Iw / 32;
   }
 
+  tr.mark("views");
   // ---- upload the join index ----
   CKS(upload(ex, ex->uid_count, h_count));
   CKS(upload(ex, ex->uid_loc, h_loc));
@@ -812,6 +854,7 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   CK(cudaMemsetAsync(ex->d_perm_max, 0, (size_t)ex->Ip * 4, ex->stream));
   CK(cudaMemsetAsync(ex->d_scalars, 0, 2 * sizeof(unsigned), ex->stream));
 
+  tr.mark("uploads");
   JoinParams jp;
   memset(&jp, 0, sizeof jp);
   jp.p0 = paths0->d_rows;
@@ -845,7 +888,7 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   const unsigned long long item_lo = sparse_k ? h_units[ub] : pair_lo, item_hi = sparse_k ? h_units[ue] : pair_hi;
   // Launch plan.  Top-K candidates are appended by the kernels only when their score beats the K-th best known so far,
   // and a launch must be able to hold every candidate it may produce:
-  //   * small joins: one launch with room for every pair;
+  //   * small joins (<= 64K pairs): one launch with room for every pair;
   //   * large joins: a short prefix (threshold unknown: every pair is a candidate) establishes the K-th score, then
   //     ONE launch covers the rest with a fixed candidate budget.  Pairs are visited in ascending (src, trg) order
   //     across launches, so later pairs only displace on a strictly greater score.  If the budget overflows (scores that
@@ -855,8 +898,8 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   std::vector<Seg> plan;
   // GCRE_TEST_SMALL_PLAN=1 (test hook) shrinks every size so the prefix / budget-overflow / redo paths run on tiny joins
   const bool tiny_plan = std::getenv("GCRE_TEST_SMALL_PLAN") != nullptr;
-  const unsigned long long small_items = std::max<unsigned long long>(1, (tiny_plan ? 128ull : (2ull << 20)) / per_item);
-  const unsigned long long prefix_items = std::max<unsigned long long>(1, (tiny_plan ? 64ull : (64ull << 10)) / per_item);
+  const unsigned long long small_items = std::max<unsigned long long>(1, (tiny_plan ? 128ull : (64ull << 10)) / per_item);
+  const unsigned long long prefix_items = std::max<unsigned long long>(1, (tiny_plan ? 64ull : (16ull << 10)) / per_item);
   const unsigned budget = tiny_plan ? 16u : (1u << 20);
   const unsigned long long redo_first = std::max<unsigned long long>(1, (tiny_plan ? 128ull : (256ull << 10)) / per_item);
   const unsigned long long redo_max = std::max<unsigned long long>(1, (tiny_plan ? 512ull : (4ull << 20)) / per_item);
@@ -935,6 +978,7 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
       }
     }
   }
+  tr.mark("launches");
   if (keep) {
     paths_res->max_half_pop = (pair_lo == 0 && pair_hi == total) ? (long long)ex->h_scalars[1] : -1;
     drop_view(paths_res);
@@ -942,6 +986,8 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
 
   CKS(emit_topk(held, top_k, out_scores, n_scores));
   if (out_perm && !(opts && opts->skip_host_perm)) CKS(gcre_exec_read_perm_max(ex, out_perm));
+  tr.mark("results");
+  tr.done(keep ? "join(keep)" : "join");
   if (opts) {
     opts->pairs_scored = pair_hi - pair_lo;
     opts->kernel_ms = kernel_ms;

@@ -26,21 +26,27 @@ namespace sparse {
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int PB = 64;          // partners per unit
-constexpr int FLUSH_AT = 240;   // carriers accumulated in the 8 bit planes before they are flushed into u16 counters
+constexpr int FLUSH_AT = 240;   // carrier slots accumulated in the 8 bit planes before they are flushed into u16 counters
+constexpr int QCAP = 96;        // per-warp queue of filtered partner carriers (drained at 64)
 }  // namespace sparse
 
 // Carrier-list (CSR) view of a path set: per (row, half) the ascending patient indices of its set bits.
+// Every list starts on an 8-entry (16-byte) boundary and is padded to a multiple of 8 entries with the sentinel
+// patient index n, whose row of the patient-major mask matrix is all zero - so lists can be consumed eight carriers
+// at a time with one 16-byte load and no tail handling.
 struct SparseView {
-  uint32_t* off = nullptr;    // [size*M + 1]
+  uint32_t* off = nullptr;    // [size*M + 1]  padded prefix (entries), multiples of 8
+  uint32_t* len = nullptr;    // [size*M]      true carrier counts
   uint16_t* car = nullptr;    // [off[size*M]]
   uint32_t* ncase = nullptr;  // [size*M] carriers < n_cases (a prefix of the ascending list)
-  size_t total = 0;
+  size_t total = 0;           // padded entries
   bool valid = false;
 };
 
 struct SparseParams {
-  const uint32_t* off0; const uint16_t* car0; const uint32_t* ncase0;
-  const uint32_t* off1; const uint16_t* car1; const uint32_t* ncase1;
+  const uint32_t* off0; const uint32_t* len0; const uint16_t* car0; const uint32_t* ncase0;
+  const uint32_t* off1; const uint32_t* len1; const uint16_t* car1; const uint32_t* ncase1;
+  int n;                                  // patients; also the sentinel carrier index (zero row of pt)
   const unsigned long long* unit_prefix;  // [U+1] running sum of ceil(count/PB)
   unsigned long long unit_begin, n_units;  // units of this launch
   unsigned long long* work_counter;
@@ -48,7 +54,9 @@ struct SparseParams {
 };
 
 // ---- view construction ----------------------------------------------------------------------------------------------
-__global__ void half_popcount_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, uint32_t* __restrict__ cnt) {
+// per (row, half): true carrier count and the padded count (multiple of 8) that is prefix-summed into offsets
+__global__ void half_popcount_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, uint32_t* __restrict__ len,
+                                     uint32_t* __restrict__ padded) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= n_items) return;
@@ -56,11 +64,14 @@ __global__ void half_popcount_kernel(const uint64_t* __restrict__ rows, long lon
   unsigned c = 0;
   for (int k = lane; k < Wp; k += 32) c += __popcll(p[k]);
   c = __reduce_add_sync(0xffffffffu, c);
-  if (lane == 0) cnt[warp] = c;
+  if (lane == 0) {
+    len[warp] = c;
+    padded[warp] = (c + 7u) & ~7u;
+  }
 }
 
-__global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, int n_cases, const uint32_t* __restrict__ off,
-                                   uint16_t* __restrict__ car, uint32_t* __restrict__ ncase) {
+__global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, int n_cases, int sentinel,
+                                   const uint32_t* __restrict__ off, uint16_t* __restrict__ car, uint32_t* __restrict__ ncase) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= n_items) return;
@@ -88,6 +99,9 @@ __global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long 
     }
     pos += __shfl_sync(0xffffffffu, incl, 31);
   }
+  // pad with the sentinel up to the next list start
+  const uint32_t end = off[warp + 1];
+  for (uint32_t o = pos + lane; o < end; o += 32) car[o] = (uint16_t)sentinel;
   nc = __reduce_add_sync(0xffffffffu, nc);
   if (lane == 0) ncase[warp] = nc;
 }
@@ -146,12 +160,15 @@ __device__ __forceinline__ int bits_for(int count) { return 32 - __clz(count); }
 template <int M, bool KEEP>
 __global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse;
-  __shared__ uint32_t s_base[WARPS][M][16][32];  // base counts per warp / half / packed register / lane
+  __shared__ uint32_t s_base[WARPS][M][16][32];          // base counts per warp / half / packed register / lane
+  __shared__ __align__(16) uint16_t s_queue[WARPS][QCAP];  // carriers of the current partner that survive the filter
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Wp = a.Wp, Iw = a.Iw;
+  const int Wp = a.Wp, Iw = a.Iw;  // Iw: words per patient row of pt (a multiple of 32: every lane owns a valid word)
   const int row_words = Wp * M;
   const unsigned long long n_work = s.n_units * (unsigned long long)s.n_perm_blocks;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint16_t* queue = s_queue[warp];
 
   float best[32];
 #pragma unroll
@@ -160,7 +177,7 @@ __global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const J
 
   auto flush_best = [&](int pb) {
     const int r0 = (pb * 32 + lane) * 32;
-    if (pb * 32 + lane < Iw) {
+    if (r0 < a.Ip) {
 #pragma unroll
       for (int b = 0; b < 32; b++)
         if (best[b] > 0.0f) atomicMax(a.perm_max + r0 + b, __float_as_int(best[b]));
@@ -185,34 +202,31 @@ __global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const J
     const uint32_t sub = (uint32_t)(unit - s.unit_prefix[idx]);
     const uint32_t cnt_idx = (uint32_t)a.count[idx];
     const uint32_t j0 = sub * PB, j1 = min(cnt_idx, j0 + PB);
-    const bool w_ok = (pb * 32 + lane) < Iw;
     const uint32_t* pt_lane = a.pt + pb * 32 + lane;
     const uint64_t* p0row = a.p0 + (size_t)idx * row_words;
+    const uint32_t loc0 = a.location[idx];
 
-    // accumulate carriers held one per lane (`c`, valid where bit set in `mask`) into the planes
     uint32_t pl[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) pl[j] = 0;
     int inbatch = 0;
-    auto add_masked = [&](uint32_t (&c16)[16], unsigned mask, uint32_t c) {
-      while (mask) {
-        uint32_t x[8];
-        int took = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const bool have = mask != 0;
-          const int src = have ? (__ffs((int)mask) - 1) : 0;
-          mask &= mask - 1;  // no-op on 0
-          const uint32_t cc = __shfl_sync(0xffffffffu, c, src);
-          x[q] = (have && w_ok) ? __ldg(pt_lane + (size_t)cc * Iw) : 0u;
-          took += have;
-        }
-        hs8(pl, x);
-        inbatch += took;
-        if (inbatch > FLUSH_AT) {
-          flush_planes(c16, pl, 8);
-          inbatch = 0;
-        }
+
+    // add the eight carriers packed in v (u16 x 8; sentinel entries hit the zero row) to the bit planes
+    auto add8 = [&](uint32_t (&c16)[16], const uint4 v) {
+      uint32_t x[8];
+      x[0] = __ldg(pt_lane + (v.x & 0xffffu) * Iw);
+      x[1] = __ldg(pt_lane + (v.x >> 16) * Iw);
+      x[2] = __ldg(pt_lane + (v.y & 0xffffu) * Iw);
+      x[3] = __ldg(pt_lane + (v.y >> 16) * Iw);
+      x[4] = __ldg(pt_lane + (v.z & 0xffffu) * Iw);
+      x[5] = __ldg(pt_lane + (v.z >> 16) * Iw);
+      x[6] = __ldg(pt_lane + (v.w & 0xffffu) * Iw);
+      x[7] = __ldg(pt_lane + (v.w >> 16) * Iw);
+      hs8(pl, x);
+      inbatch += 8;
+      if (inbatch > FLUSH_AT) {
+        flush_planes(c16, pl, 8);
+        inbatch = 0;
       }
     };
 
@@ -223,15 +237,12 @@ __global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const J
       uint32_t acc[16];
 #pragma unroll
       for (int i = 0; i < 16; i++) acc[i] = 0;
-      const uint32_t o = s.off0[(size_t)idx * M + h], len = s.off0[(size_t)idx * M + h + 1] - o;
-      t0[h] = len;
-      nc0[h] = s.ncase0[(size_t)idx * M + h];
-      for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const uint32_t c = (i < len) ? s.car0[o + i] : 0u;
-        const unsigned mask = __ballot_sync(0xffffffffu, i < len);
-        add_masked(acc, mask, c);
-      }
+      const size_t item = (size_t)idx * M + h;
+      const uint32_t o = s.off0[item], plen = s.off0[item + 1] - o;
+      t0[h] = s.len0[item];
+      nc0[h] = s.ncase0[item];
+      const uint4* lst = reinterpret_cast<const uint4*>(s.car0 + o);
+      for (uint32_t i = 0; i < plen / 8; i++) add8(acc, __ldg(lst + i));
       if (inbatch > 0) {
         flush_planes(acc, pl, bits_for(inbatch));
         inbatch = 0;
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const J
     bool base_done = false;
     // ---- partners ----
     for (uint32_t j = j0; j < j1; j++) {
-      const uint32_t loc = a.location[idx] + j;
+      const uint32_t loc = loc0 + j;
       bool flip = true;
       if (M == 2) flip = need_flip(a.path_length, a.signs, idx, loc);
       uint32_t c16[M][16];
@@ -255,20 +266,42 @@ __global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const J
         for (int i = 0; i < 16; i++) c16[h][i] = s_base[warp][h][i][lane];
         // joined half h = upstream half h | partner half hh   (src/methods.h:137-145)
         const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
-        const uint32_t o = s.off1[(size_t)loc * M + hh], len = s.off1[(size_t)loc * M + hh + 1] - o;
+        const size_t item = (size_t)loc * M + hh;
+        const uint32_t o = s.off1[item], len = s.len1[item];
         const uint64_t* p0h = p0row + h * Wp;
         nd[h] = 0;
         ncn[h] = 0;
+        uint32_t qn = 0;  // carriers waiting in the queue (warp-uniform)
         for (uint32_t i0 = 0; i0 < len; i0 += 32) {
           const uint32_t i = i0 + lane;
           const bool valid = i < len;
           const uint32_t c = valid ? s.car1[o + i] : 0u;
           const uint64_t w0 = valid ? __ldg(p0h + (c >> 6)) : 0ull;
-          const bool keep = valid && !((w0 >> (c & 63)) & 1ull);
+          const bool keep = valid && !((w0 >> (c & 63)) & 1ull);   // not already a carrier of the upstream row
           const unsigned km = __ballot_sync(0xffffffffu, keep);
-          nd[h] += __popc(km);
           ncn[h] += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
-          add_masked(c16[h], km, c);
+          if (keep) queue[qn + __popc(km & lt_mask)] = (uint16_t)c;
+          qn += __popc(km);
+          if (qn >= 64) {  // drain eight groups, move the remainder (< 32 entries) to the front
+            __syncwarp();
+#pragma unroll 1
+            for (int gq = 0; gq < 8; gq++) add8(c16[h], *reinterpret_cast<const uint4*>(queue + gq * 8));
+            const uint32_t rem = qn - 64;
+            const uint16_t keepv = (lane < rem) ? queue[64 + lane] : (uint16_t)0;
+            __syncwarp();
+            if (lane < rem) queue[lane] = keepv;
+            nd[h] += 64;
+            qn = rem;
+          }
+        }
+        nd[h] += qn;
+        if (qn > 0) {
+          // pad to a multiple of 8 with the zero row and drain
+          const uint32_t padded = (qn + 7u) & ~7u;
+          if (lane < padded - qn) queue[qn + lane] = (uint16_t)s.n;
+          __syncwarp();
+          for (uint32_t gq = 0; gq < padded / 8; gq++) add8(c16[h], *reinterpret_cast<const uint4*>(queue + gq * 8));
+          __syncwarp();
         }
         if (inbatch > 0) {
           flush_planes(c16[h], pl, bits_for(inbatch));
@@ -360,7 +393,7 @@ __global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const J
 
 static inline bool sparse_supported(int n, long long t_needed, int iters) {
   // u16 carrier indices and u16 packed counters; lanes map to permutation words, so few permutations waste lanes
-  return n <= 65536 && t_needed <= 65535 && iters > 256;
+  return n <= 65535 && t_needed <= 65535 && iters > 256;   // n itself is the sentinel carrier index (must fit u16)
 }
 
 static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count) {
