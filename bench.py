@@ -288,7 +288,8 @@ def main():
         d1.load_bits(w.gene_bits)
         d2 = ex.createPathSet(w.gene_bits2.shape[0])
         d2.load_bits(w.gene_bits2)
-        uid = {k: api.UidRelSet(lv[k].path_length, lv[k].src, lv[k].trg, lv[k].count, lv[k].location, lv[k].signs) for k in names}
+        # the join indices are inputs like the gene rows: resident on the device for the `value` measurement
+        uid = {k: api.UidRelSet(lv[k].path_length, lv[k].src, lv[k].trg, lv[k].count, lv[k].location, lv[k].signs).make_resident(ex) for k in names}
         state[method] = dict(ex=ex, d1=d1, d2=d2, uid=uid, perm_t=torch.zeros(ex.iterations, dtype=torch.float32, device="cuda"))
 
     def schedule_resident(st, results):
@@ -330,7 +331,10 @@ def main():
         out = {}
         for method in ("method1", "method2"):
             res = {}
-            out[method] = (schedule_resident(state[method], res), res)
+            info = schedule_resident(state[method], res)
+            for k in [k for k in res if k.startswith("_")]:
+                del res[k]  # kept path sets go back to the block cache now, not when the next step overwrites `last_out`
+            out[method] = (info, res)
         return out
 
     def sync_all():
@@ -347,6 +351,7 @@ def main():
     for i in range(a.warmup):
         t_dbg = time.perf_counter()
         step_resident()
+        sampler.sample()  # NVML's first queries are slow and perturb the following step: take them during warm-up
         if dbg:
             torch.cuda.synchronize()
             sys.stderr.write(f"[bench] warmup step {i}: {(time.perf_counter() - t_dbg) * 1e3:.1f} ms\n")
@@ -357,6 +362,8 @@ def main():
     gc.freeze()   # keep the interpreter's cyclic GC (hundreds of ms with torch imported) out of the timed region
     gc.disable()
     l0 = launches()
+    sampler.sm.clear()
+    sampler.reasons.clear()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     last_out = None
@@ -425,6 +432,7 @@ def main():
             d2h = 0
             for method in ("method1", "method2"):
                 ex = api.JoinExec(method, w.n_cases, w.n_ctrls, w.n_perms, device=local_rank)
+                ex.set_stream(stream.cuda_stream)
                 ex.kernel = kernel
                 ex.top_k = a.top_k
                 ex.setValueTable(table)
@@ -445,15 +453,18 @@ def main():
         sync_all()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(a.steps, 3))
-        for _ in range(e2e_steps):
+        for i in range(e2e_steps):
+            t_dbg = time.perf_counter()
             step_e2e()
+            if dbg:
+                sys.stderr.write(f"[bench] rank {rank} e2e step {i}: {(time.perf_counter() - t_dbg) * 1e3:.1f} ms\n")
         sync_all()
         dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": pp_step / float(dt.item()), "unit": "pair*perm/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_holder[0]),
                "ms_per_step": float(dt.item()) * 1e3, "steps": e2e_steps,
-               "note": "host IntegerMatrix data + CaseORControl int matrix + f64 value table uploaded every step (pinned), per method"}
+               "note": "host IntegerMatrix data + CaseORControl int matrix + f64 value table + join indices uploaded every step (pinned), per method"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

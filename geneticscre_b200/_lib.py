@@ -38,6 +38,7 @@ SYMBOLS = {
     "gcre_version": (C.c_char_p, []),
     "gcre_device_count": (_I, [C.POINTER(_I)]),
     "gcre_kernel_launch_count": (_I, [C.POINTER(C.c_uint64)]),
+    "gcre_release_cached_memory": (_I, []),
     "gcre_exec_create": (_I, [_I, _I, _I, _I, _I, C.POINTER(_VP)]),
     "gcre_exec_destroy": (_I, [_VP]),
     "gcre_exec_get_info": (_I, [_VP, C.POINTER(ExecInfoC)]),
@@ -56,6 +57,9 @@ SYMBOLS = {
     "gcre_pathset_download": (_I, [_VP, C.POINTER(C.c_uint64)]),
     "gcre_join": (_I, [_VP, _I, C.POINTER(UidRefC), _U32, C.POINTER(C.c_int32), _U32, _VP, _VP, _VP, _I, C.POINTER(ScoreC),
                        C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(JoinOptsC)]),
+    "gcre_uidset_create": (_I, [_VP, _I, C.POINTER(UidRefC), _U32, C.POINTER(C.c_int32), _U32, C.POINTER(_VP)]),
+    "gcre_uidset_destroy": (_I, [_VP]),
+    "gcre_join_uidset": (_I, [_VP, _VP, _VP, _VP, _VP, _I, C.POINTER(ScoreC), C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(JoinOptsC)]),
     "gcre_exec_device_perm_max": (_I, [_VP, C.POINTER(_VP), C.POINTER(_I)]),
     "gcre_exec_export_perm_max": (_I, [_VP, _VP, _I]),
     "gcre_exec_import_perm_max": (_I, [_VP, _VP, _I]),

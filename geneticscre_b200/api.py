@@ -63,11 +63,33 @@ class UidRelSet:
         self._packed["src"], self._packed["trg"], self._packed["count"] = self.src, self.trg, self.count
         self._packed["location"], self._packed["path_idx"] = self.location, self.path_idx
 
+        self._resident = None  # (exec, device handle) once make_resident() was called
+
     def size(self):
         return int(self.count.shape[0])
 
     def count_total_paths(self):  # src/gcre.h:83-88
         return int(self.count.sum(dtype=np.int64))
+
+    def make_resident(self, ex):
+        """Upload the join index to ``ex``'s device once; later joins with this object reuse it (extension)."""
+        self.release()
+        h = C.c_void_p()
+        check(ex._lib.gcre_uidset_create(ex._h, self.path_length, self._packed.ctypes.data_as(C.POINTER(_lib.UidRefC)), self.size(),
+                                         _ptr(self.signs, C.c_int32), self.signs.shape[0], C.byref(h)))
+        self._resident = (ex, h)
+        return self
+
+    def release(self):
+        r, self._resident = getattr(self, "_resident", None), None
+        if r is not None and r[0]._h:
+            r[0]._lib.gcre_uidset_destroy(r[1])
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class PathSet:
@@ -195,10 +217,14 @@ class JoinExec:
             opts.uid_begin, opts.uid_end = int(uid_range[0]), int(uid_range[1])
             if opts.uid_end == 0:  # empty shard at the front: nothing to do, still go through the call for the checks
                 opts.uid_begin, opts.uid_end = uids.size(), uids.size()
-        check(self._lib.gcre_join(self._h, uids.path_length, uids._packed.ctypes.data_as(C.POINTER(_lib.UidRefC)), uids.size(),
-                                  _ptr(uids.signs, C.c_int32), uids.signs.shape[0], paths0._h, paths1._h,
-                                  paths_res._h if paths_res is not None else None, int(self.top_k), sc, C.byref(n_sc),
-                                  _ptr(perm, C.c_double), C.byref(opts)))
+        res_h = paths_res._h if paths_res is not None else None
+        if uids._resident is not None and uids._resident[0] is self:
+            check(self._lib.gcre_join_uidset(self._h, uids._resident[1], paths0._h, paths1._h, res_h, int(self.top_k), sc, C.byref(n_sc),
+                                             _ptr(perm, C.c_double), C.byref(opts)))
+        else:
+            check(self._lib.gcre_join(self._h, uids.path_length, uids._packed.ctypes.data_as(C.POINTER(_lib.UidRefC)), uids.size(),
+                                      _ptr(uids.signs, C.c_int32), uids.signs.shape[0], paths0._h, paths1._h, res_h, int(self.top_k), sc,
+                                      C.byref(n_sc), _ptr(perm, C.c_double), C.byref(opts)))
         scores = [Score(s.score, s.src, s.trg, s.cases, s.ctrls) for s in sc[: n_sc.value]]
         info = {"pairs": int(opts.pairs_scored), "kernel_ms": float(opts.kernel_ms), "kernel": int(opts.kernel_used), "launches": int(opts.launches)}
         return joined_res(scores, perm[: self.iters_requested].copy(), info)

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <unordered_map>
 #include <new>
 #include <string>
@@ -80,66 +81,102 @@ static inline unsigned grid_for(long long items, int block) { return (unsigned)(
 // ------------------------------------------------------------------------------------------------------------------
 // objects
 // ------------------------------------------------------------------------------------------------------------------
-struct DevBuf {  // grow-only device scratch
+struct gcre_exec;
+
+// Process-wide, per-device cache of device blocks keyed by capacity.  Every device allocation of the engine goes through
+// it: the level schedule (and every new JoinExec of an R session) allocates and frees the same sizes over and over, and
+// going to the driver each time costs milliseconds - with the stream-ordered pool it was measured to stall for 100s of ms
+// when the pool had to grow or remap.  A block remembers the stream it was last used on and an event recorded when it was
+// freed; a different stream that reuses it first waits on that event (same scheme as PyTorch's caching allocator).
+struct CachedBlock {
+  void* p;
+  size_t cap;
+  cudaStream_t stream;
+  cudaEvent_t ev;
+};
+
+struct BlockCache {
+  std::multimap<size_t, CachedBlock> free_blocks;   // capacity -> block
+  std::unordered_map<void*, CachedBlock> live;      // blocks currently handed out
+  static size_t round_up(size_t b) { return (std::max<size_t>(b, 1) + 511) & ~(size_t)511; }
+  cudaError_t alloc(void** out, size_t bytes, cudaStream_t stream) {
+    const size_t want = round_up(bytes);
+    auto it = free_blocks.lower_bound(want);
+    if (it != free_blocks.end() && it->first <= want + want / 8) {  // at most 12.5 % slack
+      CachedBlock b = it->second;
+      free_blocks.erase(it);
+      if (b.stream != stream && b.ev) {
+        cudaError_t e = cudaStreamWaitEvent(stream, b.ev, 0);
+        if (e != cudaSuccess) return e;
+      }
+      b.stream = stream;
+      live[b.p] = b;
+      *out = b.p;
+      return cudaSuccess;
+    }
+    CachedBlock b{nullptr, want, stream, nullptr};
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e == cudaErrorMemoryAllocation && !free_blocks.empty()) {
+      cudaGetLastError();
+      release_all();
+      e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      cudaFree(b.p);
+      return e;
+    }
+    live[b.p] = b;
+    *out = b.p;
+    return cudaSuccess;
+  }
+  void free(void* p, cudaStream_t stream) {
+    if (!p) return;
+    auto it = live.find(p);
+    if (it == live.end()) {  // not ours (should not happen): hand it back to the driver
+      cudaFree(p);
+      return;
+    }
+    CachedBlock b = it->second;
+    live.erase(it);
+    b.stream = stream;
+    cudaEventRecord(b.ev, stream);
+    free_blocks.emplace(b.cap, b);
+  }
+  void release_all() {
+    for (auto& kv : free_blocks) {
+      cudaFree(kv.second.p);
+      cudaEventDestroy(kv.second.ev);
+    }
+    free_blocks.clear();
+  }
+};
+
+static std::mutex g_cache_mu;
+static std::map<int, BlockCache> g_cache;  // per device
+
+static cudaError_t dev_alloc(const gcre_exec* ex, void** out, size_t bytes);
+static void dev_free(const gcre_exec* ex, void* p);
+
+struct DevBuf {  // grow-only device scratch owned by one exec
+  const gcre_exec* owner = nullptr;
   void* p = nullptr;
   size_t cap = 0;
   int ensure(size_t bytes) {
     if (bytes <= cap) return GCRE_OK;
-    if (p) cudaFree(p);
+    dev_free(owner, p);
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 4 + 256;
-    CK(cudaMalloc(&p, want));
+    CK(dev_alloc(owner, &p, want));
     cap = want;
     return GCRE_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    dev_free(owner, p);
     p = nullptr;
     cap = 0;
-  }
-};
-
-// Size-keyed cache of device blocks for path sets and carrier-list views.  The level schedule allocates and frees the
-// same (large) sizes over and over; going to the driver each time costs milliseconds and, with the stream-ordered pool,
-// was measured to stall for 100s of ms when the pool had to grow or remap.  Blocks are only reused by work of the same
-// exec, which is serialised on one stream, so reuse needs no extra synchronisation.
-struct BlockCache {
-  std::multimap<size_t, void*> free_blocks;     // capacity -> block
-  std::unordered_map<void*, size_t> capacity;   // every block this cache ever handed out or holds
-  static size_t round_up(size_t b) { return (std::max<size_t>(b, 1) + 511) & ~(size_t)511; }
-  cudaError_t alloc(void** out, size_t bytes) {
-    const size_t want = round_up(bytes);
-    auto it = free_blocks.lower_bound(want);
-    if (it != free_blocks.end() && it->first <= want + want / 8) {  // at most 12.5 % slack
-      *out = it->second;
-      free_blocks.erase(it);
-      return cudaSuccess;
-    }
-    cudaError_t e = cudaMalloc(out, want);
-    if (e == cudaErrorMemoryAllocation && !free_blocks.empty()) {
-      cudaGetLastError();
-      release_all();
-      e = cudaMalloc(out, want);
-    }
-    if (e == cudaSuccess) capacity[*out] = want;
-    return e;
-  }
-  void free(void* p, size_t /*bytes*/) {
-    if (!p) return;
-    auto it = capacity.find(p);
-    if (it == capacity.end()) {  // not ours (should not happen): hand it back to the driver
-      cudaFree(p);
-      return;
-    }
-    free_blocks.emplace(it->second, p);
-  }
-  void release_all() {
-    for (auto& kv : free_blocks) {
-      cudaFree(kv.second);
-      capacity.erase(kv.second);
-    }
-    free_blocks.clear();
   }
 };
 
@@ -162,8 +199,7 @@ struct gcre_exec {
   // outputs / scratch
   int* d_perm_max = nullptr;
   unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total, [2..3] 64-bit work counter of the sparse kernel
-  mutable BlockCache blocks;
-  DevBuf cand, uid_count, uid_loc, uid_prefix, uid_res, uid_units, signs, scratch, scan_tmp;
+  DevBuf cand, scratch, scan_tmp;
   unsigned* h_scalars = nullptr;  // pinned
   std::vector<int32_t> h_count;   // host staging of the join index, kept across joins
   std::vector<uint32_t> h_loc;
@@ -178,18 +214,48 @@ struct gcre_pathset {
   SparseView view;             // carrier lists, built on first use by a sparse join
 };
 
+// UidRelSet (src/gcre.h:49-90) resident on the device: the flattened join index plus what the pre-checks need.
+struct gcre_uidset {
+  gcre_exec* ex = nullptr;
+  int path_length = 0;
+  uint32_t n_uids = 0, n_signs = 0;
+  unsigned long long total = 0, max_loc_end = 0, max_res_end = 0;
+  std::vector<unsigned long long> h_prefix, h_units;  // [U+1] running sums of count and of ceil(count / PB)
+  DevBuf count, loc, prefix, res, units, signs;
+};
+
 static void drop_view(gcre_pathset* ps) {
-  BlockCache& bc = ps->ex->blocks;
-  const size_t items = (size_t)ps->size * ps->ex->M;
-  bc.free(ps->view.off, (items + 1) * 4);
-  bc.free(ps->view.len, std::max<size_t>(items, 1) * 4);
-  bc.free(ps->view.ncase, std::max<size_t>(items, 1) * 4);
-  bc.free(ps->view.car, std::max<size_t>(ps->view.total, 8) * 2);
+  dev_free(ps->ex, ps->view.off);
+  dev_free(ps->ex, ps->view.len);
+  dev_free(ps->ex, ps->view.ncase);
+  dev_free(ps->ex, ps->view.car);
   ps->view = SparseView();
 }
 
 static int use_device(const gcre_exec* ex) {
   CK(cudaSetDevice(ex->device));
+  return GCRE_OK;
+}
+
+static cudaError_t dev_alloc(const gcre_exec* ex, void** out, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  return g_cache[ex->device].alloc(out, bytes, ex->stream);
+}
+
+static void dev_free(const gcre_exec* ex, void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  g_cache[ex->device].free(p, ex->stream);
+}
+
+// Return every cached (currently unused) device block to the driver.
+extern "C" int gcre_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  for (auto& kv : g_cache) {
+    cudaSetDevice(kv.first);
+    cudaDeviceSynchronize();
+    kv.second.release_all();
+  }
   return GCRE_OK;
 }
 
@@ -242,13 +308,14 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
     ex->stream = ex->own_stream;
     CK(cudaEventCreate(&ex->ev0));
     CK(cudaEventCreate(&ex->ev1));
-    CK(cudaMalloc(&ex->d_masks, std::max<size_t>((size_t)iters * ex->W64, 1) * 8));
-    CK(cudaMalloc(&ex->d_pm, (size_t)ex->Wp * ex->Ip * 8));
+    for (DevBuf* b : {&ex->cand, &ex->scratch, &ex->scan_tmp}) b->owner = ex;
+    CK(dev_alloc(ex, (void**)&ex->d_masks, std::max<size_t>((size_t)iters * ex->W64, 1) * 8));
+    CK(dev_alloc(ex, (void**)&ex->d_pm, (size_t)ex->Wp * ex->Ip * 8));
     CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)iters * ex->W64, 1) * 8, ex->stream));
     CK(cudaMemsetAsync(ex->d_pm, 0, (size_t)ex->Wp * ex->Ip * 8, ex->stream));
-    CK(cudaMalloc(&ex->d_perm_max, (size_t)ex->Ip * 4));
+    CK(dev_alloc(ex, (void**)&ex->d_perm_max, (size_t)ex->Ip * 4));
     CK(cudaMemsetAsync(ex->d_perm_max, 0, (size_t)ex->Ip * 4, ex->stream));
-    CK(cudaMalloc(&ex->d_scalars, 16 * sizeof(unsigned)));
+    CK(dev_alloc(ex, (void**)&ex->d_scalars, 16 * sizeof(unsigned)));
     CK(cudaMemsetAsync(ex->d_scalars, 0, 16 * sizeof(unsigned), ex->stream));
     CK(cudaMallocHost(&ex->h_scalars, 16 * sizeof(unsigned)));
     CK(cudaStreamSynchronize(ex->stream));
@@ -266,25 +333,12 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   if (!ex) return GCRE_OK;
   cudaSetDevice(ex->device);
   if (ex->own_stream) cudaStreamSynchronize(ex->own_stream);
-  cudaFree(ex->d_masks);
-  cudaFree(ex->d_pm);
-  cudaFree(ex->d_pt);
-  cudaFree(ex->d_vt);
-  cudaFree(ex->d_diagD);
-  cudaFree(ex->d_diagF);
-  cudaFree(ex->d_diagDM);
-  cudaFree(ex->d_perm_max);
-  cudaFree(ex->d_scalars);
+  for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
+                  (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars})
+    dev_free(ex, p);
   if (ex->h_scalars) cudaFreeHost(ex->h_scalars);
-  ex->blocks.release_all();
   ex->cand.release();
-  ex->uid_count.release();
-  ex->uid_loc.release();
-  ex->uid_prefix.release();
-  ex->uid_res.release();
-  ex->uid_units.release();
   ex->scan_tmp.release();
-  ex->signs.release();
   ex->scratch.release();
   if (ex->ev0) cudaEventDestroy(ex->ev0);
   if (ex->ev1) cudaEventDestroy(ex->ev1);
@@ -319,13 +373,13 @@ extern "C" int gcre_exec_set_value_table(gcre_exec* ex, const double* table, int
   if (rows < 0 || cols < 0) return fail(GCRE_ERR_ARG, "negative table size");
   CKS(use_device(ex));
   CK(cudaStreamSynchronize(ex->stream));
-  cudaFree(ex->d_vt);
+  dev_free(ex, ex->d_vt);
   ex->d_vt = nullptr;
   // the reference keeps at most the top-left (n+1)x(n+1) block (src/join_base.cpp:74-78); larger inputs are legal
   ex->vt_rows = rows;
   ex->vt_cols = cols;
   const size_t bytes = std::max<size_t>((size_t)rows * cols, 1) * 8;
-  CK(cudaMalloc(&ex->d_vt, bytes));
+  CK(dev_alloc(ex, (void**)&ex->d_vt, bytes));
   if ((size_t)rows * cols > 0) CK(cudaMemcpyAsync(ex->d_vt, table, (size_t)rows * cols * 8, cudaMemcpyHostToDevice, ex->stream));
   CK(cudaStreamSynchronize(ex->stream));
   ex->diag_cap = -1;  // anti-diagonal tables are rebuilt on the next join
@@ -347,7 +401,7 @@ static int rebuild_mask_layouts(gcre_exec* ex) {
 static int ensure_patient_major(gcre_exec* ex) {
   if (ex->pt_valid) return GCRE_OK;
   // n + 1 rows: row n is all zero and is what the sentinel entries that pad the carrier lists point at
-  if (!ex->d_pt) CK(cudaMalloc(&ex->d_pt, (size_t)(ex->n + 1) * ex->Iw * 4));
+  if (!ex->d_pt) CK(dev_alloc(ex, (void**)&ex->d_pt, (size_t)(ex->n + 1) * ex->Iw * 4));
   CK(cudaMemsetAsync(ex->d_pt + (size_t)ex->n * ex->Iw, 0, (size_t)ex->Iw * 4, ex->stream));
   const long long warps = (long long)ex->Iw * ((ex->n + 31) / 32);
   masks_to_patient_major_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>(ex->d_masks, ex->iters, ex->W64, ex->n, ex->d_pt, ex->Iw);
@@ -422,14 +476,14 @@ extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_path
   ps->size = size;
   const size_t bytes = (size_t)size * row_words(ex) * 8;
   if (bytes) {
-    cudaError_t e = ex->blocks.alloc((void**)&ps->d_rows, bytes);
+    cudaError_t e = dev_alloc(ex, (void**)&ps->d_rows, bytes);
     if (e != cudaSuccess) {
       delete ps;
       return fail(GCRE_ERR_NOMEM, "device allocation of %zu bytes for a path set failed: %s", bytes, cudaGetErrorString(e));
     }
     e = cudaMemsetAsync(ps->d_rows, 0, bytes, ex->stream);
     if (e != cudaSuccess) {
-      ex->blocks.free(ps->d_rows, bytes);
+      dev_free(ex, ps->d_rows);
       delete ps;
       return fail(GCRE_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
@@ -441,7 +495,7 @@ extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_path
 extern "C" int gcre_pathset_destroy(gcre_pathset* ps) {
   if (!ps) return GCRE_OK;
   cudaSetDevice(ps->ex->device);
-  ps->ex->blocks.free(ps->d_rows, (size_t)ps->size * row_words(ps->ex) * 8);  // back to the exec's block cache, no driver call
+  dev_free(ps->ex, ps->d_rows);  // back to the block cache, no driver call
   drop_view(ps);
   delete ps;
   return GCRE_OK;
@@ -608,23 +662,23 @@ static int ensure_diag(gcre_exec* ex, long long t_needed) {
   if (t_needed <= ex->diag_cap) return GCRE_OK;
   if (!ex->d_vt) {
     // no table set: the reference's value_table would be empty and indexing it is undefined; treat as all -1.0
-    CK(cudaMalloc(&ex->d_vt, 8));
+    CK(dev_alloc(ex, (void**)&ex->d_vt, 8));
     ex->vt_rows = ex->vt_cols = 0;
   }
   long long cap = std::min<long long>(ex->n, std::max<long long>(t_needed + t_needed / 4 + 64, 1024));
   cap = std::max(cap, t_needed);
   CK(cudaStreamSynchronize(ex->stream));
-  cudaFree(ex->d_diagD);
-  cudaFree(ex->d_diagF);
-  cudaFree(ex->d_diagDM);
+  dev_free(ex, ex->d_diagD);
+  dev_free(ex, ex->d_diagF);
+  dev_free(ex, ex->d_diagDM);
   ex->d_diagD = nullptr;
   ex->d_diagF = nullptr;
   ex->d_diagDM = nullptr;
   ex->diag_cap = -1;
   const size_t entries = (size_t)(cap + 1) * (size_t)(cap + 2) / 2;
-  CK(cudaMalloc(&ex->d_diagD, entries * 8));
-  if (ex->M == 1) CK(cudaMalloc(&ex->d_diagF, entries * 4));
-  else CK(cudaMalloc(&ex->d_diagDM, entries * 8));
+  CK(dev_alloc(ex, (void**)&ex->d_diagD, entries * 8));
+  if (ex->M == 1) CK(dev_alloc(ex, (void**)&ex->d_diagF, entries * 4));
+  else CK(dev_alloc(ex, (void**)&ex->d_diagDM, entries * 8));
   build_diag_kernel<<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_vt, ex->vt_rows, ex->vt_cols, (unsigned)cap, ex->d_diagD, ex->d_diagF, ex->d_diagDM);
   CK(cudaGetLastError());
       LAUNCHED();
@@ -687,9 +741,9 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
   if (ps->view.valid) return GCRE_OK;
   drop_view(ps);
   const long long items = (long long)ps->size * ex->M;
-  CK(ex->blocks.alloc((void**)&ps->view.off, (size_t)(items + 1) * 4));
-  CK(ex->blocks.alloc((void**)&ps->view.len, std::max<size_t>(items, 1) * 4));
-  CK(ex->blocks.alloc((void**)&ps->view.ncase, std::max<size_t>(items, 1) * 4));
+  CK(dev_alloc(ex, (void**)&ps->view.off, (size_t)(items + 1) * 4));
+  CK(dev_alloc(ex, (void**)&ps->view.len, std::max<size_t>(items, 1) * 4));
+  CK(dev_alloc(ex, (void**)&ps->view.ncase, std::max<size_t>(items, 1) * 4));
   CK(cudaMemsetAsync(ps->view.off, 0, (size_t)(items + 1) * 4, ex->stream));
   uint32_t total = 0;
   if (items > 0) {
@@ -709,7 +763,7 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
     CK(cudaStreamSynchronize(ex->stream));
   }
   ps->view.total = total;
-  CK(ex->blocks.alloc((void**)&ps->view.car, std::max<size_t>(total, 8) * 2));
+  CK(dev_alloc(ex, (void**)&ps->view.car, std::max<size_t>(total, 8) * 2));
   if (items > 0) {
     build_lists_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ex->n, ps->view.off, ps->view.car,
                                                                          ps->view.ncase);
@@ -723,13 +777,6 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
 // ------------------------------------------------------------------------------------------------------------------
 // join
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T>
-static int upload(gcre_exec* ex, DevBuf& buf, const std::vector<T>& v) {
-  CKS(buf.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
-  if (!v.empty()) CK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ex->stream));
-  return GCRE_OK;
-}
-
 static int launch_join_dense(gcre_exec* ex, const JoinParams& jp, bool keep, int* launches) {
   const unsigned long long n_pairs = jp.pair_end - jp.pair_begin;
   if (n_pairs == 0) return GCRE_OK;
@@ -750,48 +797,140 @@ static int launch_join_dense(gcre_exec* ex, const JoinParams& jp, bool keep, int
   return GCRE_OK;
 }
 
+static int build_uidset(gcre_exec* ex, int path_length, const gcre_uid_ref* uids, uint32_t n_uids, const int32_t* signs, uint32_t n_signs,
+                        gcre_uidset* us) {
+  us->ex = ex;
+  for (DevBuf* b : {&us->count, &us->loc, &us->prefix, &us->res, &us->units, &us->signs}) b->owner = ex;
+  us->path_length = path_length;
+  us->n_uids = n_uids;
+  us->n_signs = n_signs;
+  std::vector<int32_t>& h_count = ex->h_count;
+  std::vector<uint32_t>& h_loc = ex->h_loc;
+  std::vector<unsigned long long>& h_res = ex->h_res;
+  h_count.resize(n_uids);
+  h_loc.resize(n_uids);
+  h_res.resize(n_uids);
+  us->h_prefix.resize((size_t)n_uids + 1);
+  us->h_units.resize((size_t)n_uids + 1);
+  unsigned long long total = 0, nu = 0;
+  for (uint32_t u = 0; u < n_uids; u++) {
+    const int32_t c = uids[u].count > 0 ? uids[u].count : 0;
+    h_count[u] = c;
+    h_loc[u] = uids[u].location;
+    h_res[u] = uids[u].path_idx;
+    us->h_prefix[u] = total;
+    us->h_units[u] = nu;
+    if (c > 0) {
+      us->max_loc_end = std::max(us->max_loc_end, (unsigned long long)uids[u].location + c);
+      us->max_res_end = std::max(us->max_res_end, (unsigned long long)uids[u].path_idx + c);
+    }
+    total += c;
+    nu += ((unsigned long long)c + sparse::PB - 1) / sparse::PB;
+  }
+  us->h_prefix[n_uids] = total;
+  us->h_units[n_uids] = nu;
+  us->total = total;
+  auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> int {
+    CKS(buf.ensure(std::max<size_t>(bytes, 8)));
+    if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ex->stream));
+    return GCRE_OK;
+  };
+  CKS(up(us->count, h_count.data(), (size_t)n_uids * 4));
+  CKS(up(us->loc, h_loc.data(), (size_t)n_uids * 4));
+  CKS(up(us->res, h_res.data(), (size_t)n_uids * 8));
+  CKS(up(us->prefix, us->h_prefix.data(), ((size_t)n_uids + 1) * 8));
+  CKS(up(us->units, us->h_units.data(), ((size_t)n_uids + 1) * 8));
+  CKS(up(us->signs, signs, (size_t)n_signs * 4));
+  CK(cudaStreamSynchronize(ex->stream));  // the staging vectors are reused by the next index
+  return GCRE_OK;
+}
+
+static void free_uidset_buffers(gcre_uidset* us) {
+  us->count.release();
+  us->loc.release();
+  us->prefix.release();
+  us->res.release();
+  us->units.release();
+  us->signs.release();
+}
+
+extern "C" int gcre_uidset_create(gcre_exec* ex, int path_length, const gcre_uid_ref* uids, uint32_t n_uids, const int32_t* signs,
+                                  uint32_t n_signs, gcre_uidset** out) {
+  if (!ex || !out || (!uids && n_uids) || (!signs && n_signs)) return fail(GCRE_ERR_ARG, "null argument");
+  *out = nullptr;
+  CKS(use_device(ex));
+  gcre_uidset* us = new (std::nothrow) gcre_uidset();
+  if (!us) return fail(GCRE_ERR_NOMEM, "host allocation failed");
+  const int rc = build_uidset(ex, path_length, uids, n_uids, signs, n_signs, us);
+  if (rc != GCRE_OK) {
+    free_uidset_buffers(us);
+    delete us;
+    return rc;
+  }
+  *out = us;
+  return GCRE_OK;
+}
+
+extern "C" int gcre_uidset_destroy(gcre_uidset* us) {
+  if (!us) return GCRE_OK;
+  cudaSetDevice(us->ex->device);
+  cudaStreamSynchronize(us->ex->stream);
+  free_uidset_buffers(us);
+  delete us;
+  return GCRE_OK;
+}
+
+static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* paths0, const gcre_pathset* paths1, gcre_pathset* paths_res,
+                     int top_k, gcre_score* out_scores, int* n_scores, double* out_perm, gcre_join_opts* opts, PhaseTrace& tr);
+
 extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uids, uint32_t n_uids, const int32_t* signs, uint32_t n_signs,
                          const gcre_pathset* paths0, const gcre_pathset* paths1, gcre_pathset* paths_res, int top_k, gcre_score* out_scores,
                          int* n_scores, double* out_perm, gcre_join_opts* opts) {
   if (!ex || !paths0 || !paths1 || !out_scores || !n_scores || (!uids && n_uids) || (!signs && n_signs))
     return fail(GCRE_ERR_ARG, "null argument");
+  CKS(use_device(ex));
+  PhaseTrace tr;
+  // src/join_base.cpp:196: check_equal(uids.size(), paths0.size) - before any work on the index
+  if (n_uids != paths0->size) return fail(GCRE_ERR_ASSERT, "assertion");
+  gcre_uidset us;
+  int rc = build_uidset(ex, path_length, uids, n_uids, signs, n_signs, &us);
+  tr.mark("index");
+  if (rc == GCRE_OK) rc = join_impl(ex, &us, paths0, paths1, paths_res, top_k, out_scores, n_scores, out_perm, opts, tr);
+  if (rc == GCRE_OK) cudaStreamSynchronize(ex->stream);
+  free_uidset_buffers(&us);
+  return rc;
+}
+
+extern "C" int gcre_join_uidset(gcre_exec* ex, const gcre_uidset* uidset, const gcre_pathset* paths0, const gcre_pathset* paths1,
+                                gcre_pathset* paths_res, int top_k, gcre_score* out_scores, int* n_scores, double* out_perm,
+                                gcre_join_opts* opts) {
+  if (!ex || !uidset || !paths0 || !paths1 || !out_scores || !n_scores) return fail(GCRE_ERR_ARG, "null argument");
+  if (uidset->ex != ex) return fail(GCRE_ERR_ARG, "join index belongs to another exec");
+  CKS(use_device(ex));
+  PhaseTrace tr;
+  return join_impl(ex, uidset, paths0, paths1, paths_res, top_k, out_scores, n_scores, out_perm, opts, tr);
+}
+
+static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* paths0, const gcre_pathset* paths1, gcre_pathset* paths_res,
+                     int top_k, gcre_score* out_scores, int* n_scores, double* out_perm, gcre_join_opts* opts, PhaseTrace& tr) {
   if (!out_perm && ex->iters > 0 && !(opts && opts->skip_host_perm)) return fail(GCRE_ERR_ARG, "null argument");
   if (paths0->ex != ex || paths1->ex != ex || (paths_res && paths_res->ex != ex)) return fail(GCRE_ERR_ARG, "path set belongs to another exec");
-  CKS(use_device(ex));
   if (top_k < 1) top_k = 1;
   const bool keep = paths_res && paths_res->size != 0;
-  PhaseTrace tr;
+  const uint32_t n_uids = us->n_uids, n_signs = us->n_signs;
+  const int path_length = us->path_length;
+  const unsigned long long total = us->total;
+  const std::vector<unsigned long long>& h_prefix = us->h_prefix;
+  const std::vector<unsigned long long>& h_units = us->h_units;
 
   // ---- pre-checks, src/join_base.cpp:196-200 ----
   if (n_uids != paths0->size) return fail(GCRE_ERR_ASSERT, "assertion");
-  std::vector<int32_t>& h_count = ex->h_count;
-  std::vector<uint32_t>& h_loc = ex->h_loc;
-  std::vector<unsigned long long>&h_prefix = ex->h_prefix, &h_res = ex->h_res;
-  h_count.resize(n_uids);
-  h_loc.resize(n_uids);
-  h_prefix.resize((size_t)n_uids + 1);
-  h_res.resize(n_uids);
-  unsigned long long total = 0;
-  unsigned long long max_loc_end = 0;
-  for (uint32_t u = 0; u < n_uids; u++) {
-    const int32_t c = uids[u].count > 0 ? uids[u].count : 0;
-    h_count[u] = c;
-    h_loc[u] = uids[u].location;
-    h_prefix[u] = total;
-    h_res[u] = uids[u].path_idx;
-    if (c > 0) {
-      const unsigned long long last = (unsigned long long)uids[u].location + c - 1;
-      if (last >= paths1->size) return fail(GCRE_ERR_RANGE, "assertion");
-      max_loc_end = std::max(max_loc_end, last + 1);
-      if (keep && uids[u].path_idx + c > paths_res->size) return fail(GCRE_ERR_RANGE, "assertion");
-    }
-    total += c;
-  }
-  h_prefix[n_uids] = total;
   if (paths_res && !(paths_res->size == 0 || paths_res->size == total)) return fail(GCRE_ERR_ASSERT, "assertion");
+  if (us->max_loc_end > paths1->size) return fail(GCRE_ERR_RANGE, "assertion");
+  if (keep && us->max_res_end > paths_res->size) return fail(GCRE_ERR_RANGE, "assertion");
   if (ex->M == 2 && total > 0) {
     // need_flip indexes signs by upstream row and/or partner row (src/gcre.h:71-81); the reference reads unchecked
-    const unsigned long long need = path_length > 3 ? n_uids : (path_length < 3 ? max_loc_end : std::max<unsigned long long>(n_uids, max_loc_end));
+    const unsigned long long need = path_length > 3 ? n_uids : (path_length < 3 ? us->max_loc_end : std::max<unsigned long long>(n_uids, us->max_loc_end));
     if (n_signs < need) return fail(GCRE_ERR_RANGE, "assertion");
   }
 
@@ -820,41 +959,22 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, 1 << 30)) kernel = GCRE_KERNEL_DENSE;
   SparseParams sp;
   memset(&sp, 0, sizeof sp);
-  std::vector<unsigned long long>& h_units = ex->h_units;
-  h_units.clear();
   if (kernel == GCRE_KERNEL_SPARSE) {
     CKS(ensure_patient_major(ex));
     CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths0)));
     CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths1)));
-    h_units.resize((size_t)n_uids + 1);
-    unsigned long long nu = 0;
-    for (uint32_t u = 0; u < n_uids; u++) {
-      h_units[u] = nu;
-      nu += ((unsigned long long)h_count[u] + sparse::PB - 1) / sparse::PB;
-    }
-    h_units[n_uids] = nu;
-    CKS(upload(ex, ex->uid_units, h_units));
     sp.off0 = paths0->view.off; sp.len0 = paths0->view.len; sp.car0 = paths0->view.car; sp.ncase0 = paths0->view.ncase;
     sp.off1 = paths1->view.off; sp.len1 = paths1->view.len; sp.car1 = paths1->view.car; sp.ncase1 = paths1->view.ncase;
     sp.n = ex->n;
-    sp.unit_prefix = (const unsigned long long*)ex->uid_units.p;
+    sp.unit_prefix = (const unsigned long long*)us->units.p;
     sp.work_counter = (unsigned long long*)(ex->d_scalars + 2);
     sp.n_perm_blocks = ex->Iw / 32;
   }
 
   tr.mark("views");
-  // ---- upload the join index ----
-  CKS(upload(ex, ex->uid_count, h_count));
-  CKS(upload(ex, ex->uid_loc, h_loc));
-  CKS(upload(ex, ex->uid_prefix, h_prefix));
-  CKS(upload(ex, ex->uid_res, h_res));
-  CKS(ex->signs.ensure(std::max<size_t>(n_signs, 1) * 4));
-  if (n_signs) CK(cudaMemcpyAsync(ex->signs.p, signs, (size_t)n_signs * 4, cudaMemcpyHostToDevice, ex->stream));
-
   CK(cudaMemsetAsync(ex->d_perm_max, 0, (size_t)ex->Ip * 4, ex->stream));
   CK(cudaMemsetAsync(ex->d_scalars, 0, 2 * sizeof(unsigned), ex->stream));
 
-  tr.mark("uploads");
   JoinParams jp;
   memset(&jp, 0, sizeof jp);
   jp.p0 = paths0->d_rows;
@@ -862,12 +982,12 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
   jp.pres = keep ? paths_res->d_rows : nullptr;
   jp.Wp = ex->Wp;
   jp.n_cases = ex->n_cases;
-  jp.count = (const int32_t*)ex->uid_count.p;
-  jp.location = (const uint32_t*)ex->uid_loc.p;
-  jp.prefix = (const unsigned long long*)ex->uid_prefix.p;
-  jp.res_idx = (const unsigned long long*)ex->uid_res.p;
+  jp.count = (const int32_t*)us->count.p;
+  jp.location = (const uint32_t*)us->loc.p;
+  jp.prefix = (const unsigned long long*)us->prefix.p;
+  jp.res_idx = (const unsigned long long*)us->res.p;
   jp.n_uids = n_uids;
-  jp.signs = (const int32_t*)ex->signs.p;
+  jp.signs = (const int32_t*)us->signs.p;
   jp.path_length = path_length;
   jp.pm = ex->d_pm;
   jp.pt = ex->d_pt;

@@ -44,7 +44,16 @@ def merge_shard_result(res, top_k: int, merge_topk, score_cls, dist, device_perm
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the one data-path collective of a join
     n = t.numel() if n_perms is None else n_perms
     res.permuted_scores = t[:n].to(torch.float64).cpu().numpy()
-    gathered = [None] * world
-    dist.all_gather_object(gathered, [(s.score, s.src, s.trg, s.cases, s.ctrls) for s in res.scores])
-    res.scores = merge_topk([[score_cls(*e) for e in g] for g in gathered], top_k)
+    # top-K lists as fixed-size tensors (K + 1 rows of score, src, trg, cases, ctrls; unused rows hold NaN)
+    rows = torch.full((top_k + 1, 5), float("nan"), dtype=torch.float64)
+    for i, sc in enumerate(res.scores[: top_k + 1]):
+        rows[i] = torch.tensor([sc.score, sc.src, sc.trg, sc.cases, sc.ctrls], dtype=torch.float64)
+    rows = rows.to(t.device)
+    gathered = [torch.empty_like(rows) for _ in range(world)]
+    dist.all_gather(gathered, rows)
+    lists = []
+    for gt in gathered:
+        gt = gt.cpu().numpy()
+        lists.append([score_cls(float(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4])) for r in gt if not np.isnan(r[1])])
+    res.scores = merge_topk(lists, top_k)
     return res

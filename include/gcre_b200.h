@@ -89,6 +89,8 @@ const char* gcre_version(void);
 int gcre_device_count(int* count);
 /* Number of CUDA kernels this library has launched in this process so far (all execs, all streams). */
 int gcre_kernel_launch_count(uint64_t* count);
+/* Device memory freed by execs / path sets is kept in a per-device cache for reuse; this returns it to the driver. */
+int gcre_release_cached_memory(void);
 
 /* JoinExec::JoinExec(method_name, num_cases, num_ctrls, iters)  (src/join_base.cpp:37-59).
  * method: 1 = "method1", 2 = anything else (JoinExec::to_method, src/gcre.h:125-133).  device: CUDA ordinal. */
@@ -149,6 +151,16 @@ int gcre_pathset_download(const gcre_pathset* ps, uint64_t* out);
 int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uids, uint32_t n_uids, const int32_t* signs,
               uint32_t n_signs, const gcre_pathset* paths0, const gcre_pathset* paths1, gcre_pathset* paths_res,
               int top_k, gcre_score* out_scores, int* n_scores, double* out_perm, gcre_join_opts* opts);
+
+/* UidRelSet kept on the device: build the join index once, join with it many times (the level schedule of a run reuses
+ * nothing, but a resident service / benchmark does).  gcre_join(...) == create + gcre_join_uidset + destroy. */
+typedef struct gcre_uidset gcre_uidset;
+int gcre_uidset_create(gcre_exec* ex, int path_length, const gcre_uid_ref* uids, uint32_t n_uids, const int32_t* signs,
+                       uint32_t n_signs, gcre_uidset** out);
+int gcre_uidset_destroy(gcre_uidset* uidset);
+int gcre_join_uidset(gcre_exec* ex, const gcre_uidset* uidset, const gcre_pathset* paths0, const gcre_pathset* paths1,
+                     gcre_pathset* paths_res, int top_k, gcre_score* out_scores, int* n_scores, double* out_perm,
+                     gcre_join_opts* opts);
 
 /* Device pointer (float[iterations]) to the permutation maxima of the last join on this exec -- lets a multi-GPU
  * driver merge shards with one allreduce(max) (NCCL) without a host round trip.  Valid until the next join. */
