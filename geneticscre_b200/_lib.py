@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libgcre_b200.so")
+LIB_PATH = os.environ.get("GCRE_B200_LIB") or os.path.join(PKG, "libgcre_b200.so")  # override: A/B builds during tuning
 
 GCRE_OK, GCRE_ERR_ASSERT, GCRE_ERR_RANGE, GCRE_ERR_ARG, GCRE_ERR_CUDA, GCRE_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 KERNEL_AUTO, KERNEL_DENSE, KERNEL_SPARSE = 0, 1, 2

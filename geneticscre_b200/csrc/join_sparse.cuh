@@ -23,11 +23,16 @@
 namespace gcre {
 
 namespace sparse {
-constexpr int THREADS = 256;
+constexpr int THREADS = 128;
 constexpr int WARPS = THREADS / 32;
 constexpr int PB = 64;          // partners per unit
 constexpr int FLUSH_AT = 240;   // carrier slots accumulated in the 8 bit planes before they are flushed into u16 counters
 constexpr int QCAP = 96;        // per-warp queue of filtered partner carriers (drained at 64)
+// Resident CTAs per SM asked of ptxas (= register budget).  Measured on B200 with the level-4 join of BASELINE config 3
+// (12 M pairs, ms per launch): method 1: 4 CTAs (128 regs) 19.9, 5: 17.4, 6: 16.2, 8 (64 regs, 164 B spilled) 15.0;
+// method 2: 4: 33.9, 5: 39.1, 6: 40.2, 8: 40.0.  Keeping the per-permutation state in shared memory instead (no
+// spills at 48 regs, 1,000 SASS instructions) was slower for both (22 / 35 ms): the kernel is issue-bound.
+constexpr int min_blocks(int m) { return m == 1 ? 8 : 4; }
 }  // namespace sparse
 
 // Carrier-list (CSR) view of a path set: per (row, half) the ascending patient indices of its set bits.
@@ -158,7 +163,7 @@ __device__ __forceinline__ int bits_for(int count) { return 32 - __clz(count); }
 #define GCRE_C16_HI(b) (((b) >> 3) & 1)
 
 template <int M, bool KEEP>
-__global__ void __launch_bounds__(sparse::THREADS, 2) join_sparse_kernel(const JoinParams a, const SparseParams s) {
+__global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_sparse_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse;
   __shared__ uint32_t s_base[WARPS][M][16][32];          // base counts per warp / half / packed register / lane
   __shared__ __align__(16) uint16_t s_queue[WARPS][QCAP];  // carriers of the current partner that survive the filter
@@ -400,7 +405,7 @@ static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinPara
   const unsigned long long n_work = sp.n_units * (unsigned long long)sp.n_perm_blocks;
   if (n_work == 0) return cudaSuccess;
   const unsigned long long want = (n_work + sparse::WARPS - 1) / sparse::WARPS;
-  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * 2);
+  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * sparse::min_blocks(M));
   if (M == 1) {
     if (keep) join_sparse_kernel<1, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
     else join_sparse_kernel<1, false><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);

@@ -6,6 +6,7 @@ from geneticscre_b200 import api, synth, _lib
 import bench
 class A: pass
 a = A(); a.__dict__.update(bench.WORKLOAD)
+if len(sys.argv) > 2: a.n_edges = int(sys.argv[2])
 w, _ = bench.make_workload(a)
 lv = w.net.levels
 kernel = {"dense": 1, "sparse": 2}[sys.argv[1] if len(sys.argv) > 1 else "sparse"]
