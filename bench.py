@@ -17,9 +17,14 @@ in the checkout; sizes generated are reported in `config`).  One step = the whol
   cpu_baseline  the reference's own join (oracle/_ref, built from the unmodified reference sources with
              g++ -O3 -march=<host level> -mpopcnt) on all host cores over a bounded sample of the same level-4 join
 
-Multi-GPU (N > 1): levels 1-3 are computed redundantly per rank (tiny), the level-4 upstream rows are sharded by pair
-count, permutation maxima are merged with ONE NCCL allreduce(max), top-K lists with an all-gather + merge.  Fixed total
-work => "scaling": "strong".
+Multi-GPU (N > 1), one process per GPU:
+  --shard perms (default)  every GPU scores ALL pairs against its own block of n_perms permutations (the decomposition of
+             BASELINE config 4/5: more permutations, same cohort); per-permutation maxima are concatenated with one
+             all-gather, top-K is identical on every rank.  Per-GPU work is fixed => "scaling": "weak"; value counts
+             N x n_perms permutations.
+  --shard rows             the last level's upstream rows are split by pair count, levels 1-3 are computed redundantly,
+             permutation maxima are merged with ONE NCCL allreduce(max) per join, top-K lists with an all-gather +
+             merge.  Fixed total work => "scaling": "strong".
 """
 from __future__ import annotations
 
@@ -46,6 +51,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "dense", "sparse"])
+    ap.add_argument("--shard", default="perms", choices=["perms", "rows"],
+                    help="N > 1: 'perms' = every GPU scores all pairs against its own block of n_perms permutations (weak scaling, "
+                         "results concatenated); 'rows' = the last level's upstream rows are split, maxima merged with one NCCL allreduce(max)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per method for the baseline sample")
@@ -260,6 +268,10 @@ def main():
     kernel = {"auto": _lib.KERNEL_AUTO, "dense": _lib.KERNEL_DENSE, "sparse": _lib.KERNEL_SPARSE}[a.kernel]
 
     w, gen_s = make_workload(a)
+    shard_perms = world > 1 and a.shard == "perms"
+    if shard_perms and rank > 0:
+        # this rank's own block of permutations (same cohort, network and table on every rank)
+        w.perm_masks = synth.make_perm_masks(w.n_cases, w.n_ctrls, w.n_perms, a.seed + 3 + 1000 * rank)
     lv = w.net.levels
     n = w.n_patients
     names = ["1a", "1b", "2", "3", "4", "5"][: a.path_length + 1]
@@ -290,7 +302,8 @@ def main():
         d2.load_bits(w.gene_bits2)
         # the join indices are inputs like the gene rows: resident on the device for the `value` measurement
         uid = {k: api.UidRelSet(lv[k].path_length, lv[k].src, lv[k].trg, lv[k].count, lv[k].location, lv[k].signs).make_resident(ex) for k in names}
-        state[method] = dict(ex=ex, d1=d1, d2=d2, uid=uid, perm_t=torch.zeros(ex.iterations, dtype=torch.float32, device="cuda"))
+        state[method] = dict(ex=ex, d1=d1, d2=d2, uid=uid, perm_t=torch.zeros(ex.iterations, dtype=torch.float32, device="cuda"),
+                             perm_all=torch.zeros(ex.iterations * world, dtype=torch.float32, device="cuda"))
 
     def schedule_resident(st, results):
         """Levels 1a,1b,2,3,(4,5) with device-resident inputs; the last level is sharded across ranks."""
@@ -310,7 +323,12 @@ def main():
             else:
                 operand = results["_p3"]
             res_set = ex.createPathSet(lv[k].n_pairs) if (keep or (k in ("2", "3") and a.path_length > int(k))) else zero
-            if k == last and world > 1:
+            if k == last and shard_perms:
+                r = ex.join(uid[k], prev, operand, res_set)
+                # result assembly: the per-permutation maxima of all blocks are concatenated (no reduction needed)
+                _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations))
+                dist.all_gather_into_tensor(st["perm_all"], st["perm_t"])
+            elif k == last and world > 1:
                 r = ex.join(uid[k], prev, operand, zero, uid_range=my_shard, skip_host_perm=True)
                 _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations))
                 # ONE data-path collective per join: NCCL allreduce(max) of the f32 maxima (+ a K-entry gather)
@@ -383,7 +401,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_step = float(t_ms.item()) / a.steps
-    pp_step = pairs_per_step(w, a.path_length) * w.n_perms
+    pp_step = pairs_per_step(w, a.path_length) * w.n_perms * (world if shard_perms else 1)  # whole job, all ranks
     value = pp_step / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel: the last-level join of each method, timed live by CUDA events inside join ----
@@ -439,7 +457,7 @@ def main():
                 ex.setPermutedCases(perm_i)
                 d1 = ex.createPathSet(data1_i.shape[0]); d1.load(data1_i)
                 d2 = ex.createPathSet(data2_i.shape[0]); d2.load(data2_i)
-                st = dict(ex=ex, d1=d1, d2=d2, uid=state[method]["uid"], perm_t=state[method]["perm_t"])
+                st = dict(ex=ex, d1=d1, d2=d2, uid=state[method]["uid"], perm_t=state[method]["perm_t"], perm_all=state[method]["perm_all"])
                 res = {}
                 schedule_resident(st, res)
                 for k, r in res.items():
@@ -474,9 +492,14 @@ def main():
             cpu = {"value": None, "unit": "pair*perm/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}
 
     if rank == 0:
+        cfg = workload_config(a, w)
+        cfg["permutations_total"] = w.n_perms * (world if shard_perms else 1)
+        cfg["parallelism"] = ("1 GPU" if world == 1 else
+                              f"{world} GPUs, one block of {w.n_perms} permutations per GPU over all pairs; maxima concatenated (all-gather)" if shard_perms else
+                              f"{world} GPUs, level-{last} upstream rows sharded by pair count; one NCCL allreduce(max) per join + top-K gather")
         line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "u64 bitsets, u32 counts, f64 scores", "data": "synthetic", "config": workload_config(a, w), "clocks": clocks,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (shard_perms or world == 1) else "strong", "vs_baseline": None,
+                "dtype": "u64 bitsets, u32 counts, f64 scores", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu,
                 "pair_perm_per_step": pp_step, "workload_gen_s": round(gen_s, 1)}
         print(json.dumps(line))
