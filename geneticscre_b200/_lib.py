@@ -44,6 +44,9 @@ SYMBOLS = {
     "gcre_exec_get_info": (_I, [_VP, C.POINTER(ExecInfoC)]),
     "gcre_exec_set_stream": (_I, [_VP, _VP]),
     "gcre_exec_set_value_table": (_I, [_VP, C.POINTER(C.c_double), _I, _I]),
+    "gcre_exec_generate_value_table": (_I, [_VP]),
+    "gcre_log_factorial_table": (_I, [_I, C.POINTER(C.c_double)]),
+    "gcre_exec_get_value_table": (_I, [_VP, C.POINTER(C.c_double), _I, _I]),
     "gcre_exec_set_permuted_cases_i32": (_I, [_VP, C.POINTER(C.c_int32), _I, _I]),
     "gcre_exec_set_permuted_masks_u64": (_I, [_VP, C.POINTER(C.c_uint64), _I]),
     "gcre_pathset_create": (_I, [_VP, _U32, C.POINTER(_VP)]),

@@ -187,6 +187,15 @@ class JoinExec:
             t = t.reshape(0, 0)
         check(self._lib.gcre_exec_set_value_table(self._h, _ptr(t, C.c_double), t.shape[0], t.shape[1]))
 
+    def generateValueTable(self):
+        """getValuesTable (R/Utils.R:137-159) on the device for this exec's (num_cases, num_ctrls) (extension)."""
+        check(self._lib.gcre_exec_generate_value_table(self._h))
+
+    def getValueTable(self):
+        out = np.zeros((self.num_cases + 1, self.num_ctrls + 1), dtype=np.float64)
+        check(self._lib.gcre_exec_get_value_table(self._h, _ptr(out, C.c_double), out.shape[0], out.shape[1]))
+        return out
+
     def setPermutedCases(self, perm_cases):
         p = _as(perm_cases, np.int32)
         rows = p.shape[0]

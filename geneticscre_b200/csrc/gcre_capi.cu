@@ -22,6 +22,7 @@
 #include "setup_kernels.cuh"
 #include "join_dense.cuh"
 #include "join_sparse.cuh"
+#include "value_table.cuh"
 
 using namespace gcre;
 
@@ -383,6 +384,67 @@ extern "C" int gcre_exec_set_value_table(gcre_exec* ex, const double* table, int
   if ((size_t)rows * cols > 0) CK(cudaMemcpyAsync(ex->d_vt, table, (size_t)rows * cols * 8, cudaMemcpyHostToDevice, ex->stream));
   CK(cudaStreamSynchronize(ex->stream));
   ex->diag_cap = -1;  // anti-diagonal tables are rebuilt on the next join
+  return GCRE_OK;
+}
+
+// log(k!) for k = 0..n with this library's std::lgamma - the table both value-table generators (device and the numpy
+// restatement) start from, so that they make identical "probability <= own" decisions at exact ties.
+extern "C" int gcre_log_factorial_table(int n, double* out) {
+  if (!out || n < 0) return fail(GCRE_ERR_ARG, "bad argument");
+  for (int k = 0; k <= n; k++) out[k] = std::lgamma((double)k + 1.0);
+  return GCRE_OK;
+}
+
+// getValuesTable (R/Utils.R:137-159) on the device: fills this exec's value table for its own (num_cases, num_ctrls).
+extern "C" int gcre_exec_generate_value_table(gcre_exec* ex) {
+  if (!ex) return fail(GCRE_ERR_ARG, "null argument");
+  CKS(use_device(ex));
+  CK(cudaStreamSynchronize(ex->stream));
+  const int nc = ex->n_cases, nt = ex->n_ctrls, n = ex->n;
+  const size_t entries = (size_t)(nc + 1) * (nt + 1);
+  dev_free(ex, ex->d_vt);
+  ex->d_vt = nullptr;
+  CK(dev_alloc(ex, (void**)&ex->d_vt, entries * 8));
+  ex->vt_rows = nc + 1;
+  ex->vt_cols = nt + 1;
+  ex->diag_cap = -1;
+  // log-factorials on the host (the same std::lgamma values the numpy restatement uses via math.lgamma)
+  std::vector<double> lf((size_t)n + 1);
+  gcre_log_factorial_table(n, lf.data());
+  const int m_max = std::min(nc, nt) + 1;
+  const int blocks = std::min(n + 1, ex->sm_count * 8);
+  double* d_lf = nullptr;
+  double* d_scratch = nullptr;
+  unsigned long long* d_key = nullptr;
+  int rc = [&]() -> int {
+    CK(dev_alloc(ex, (void**)&d_lf, ((size_t)n + 1) * 8));
+    CK(dev_alloc(ex, (void**)&d_scratch, (size_t)blocks * 3 * m_max * 8));
+    CK(dev_alloc(ex, (void**)&d_key, 8));
+    CK(cudaMemcpyAsync(d_lf, lf.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ex->stream));
+    CK(cudaMemsetAsync(d_key, 0, 8, ex->stream));
+    // entries no diagonal reaches do not exist in an (nc+1) x (nt+1) table: every (x, y) has total x + y <= n
+    value_table_kernel<<<blocks, VT_THREADS, 0, ex->stream>>>(d_lf, nc, nt, ex->d_vt, d_scratch, m_max, d_key);
+    CK(cudaGetLastError());
+      LAUNCHED();
+    value_table_fixup_kernel<<<ex->sm_count * 8, 256, 0, ex->stream>>>(ex->d_vt, entries, d_key);
+    CK(cudaGetLastError());
+      LAUNCHED();
+    CK(cudaStreamSynchronize(ex->stream));
+    return GCRE_OK;
+  }();
+  dev_free(ex, d_lf);
+  dev_free(ex, d_scratch);
+  dev_free(ex, d_key);
+  return rc;
+}
+
+// Copy the exec's value table (as supplied or generated) to the host: rows x cols doubles, row-major.
+extern "C" int gcre_exec_get_value_table(const gcre_exec* ex, double* out, int rows, int cols) {
+  if (!ex || !out) return fail(GCRE_ERR_ARG, "null argument");
+  if (rows != ex->vt_rows || cols != ex->vt_cols || !ex->d_vt) return fail(GCRE_ERR_ASSERT, "assertion");
+  CKS(use_device(ex));
+  CK(cudaMemcpyAsync(out, ex->d_vt, (size_t)rows * cols * 8, cudaMemcpyDeviceToHost, ex->stream));
+  CK(cudaStreamSynchronize(ex->stream));
   return GCRE_OK;
 }
 

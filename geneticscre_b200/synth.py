@@ -92,32 +92,48 @@ def make_perm_masks(n_cases: int, n_ctrls: int, n_perms: int, seed: int) -> np.n
     return out
 
 
+def log_factorials(n: int) -> np.ndarray:
+    """log(k!) for k = 0..n.  Taken from the engine library's host routine when it is built (so the device generator and
+    this restatement decide exact probability ties identically), else from math.lgamma."""
+    try:
+        import ctypes
+
+        from . import _lib
+
+        out = np.zeros(n + 1, dtype=np.float64)
+        _lib.check(_lib.load().gcre_log_factorial_table(int(n), out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return out
+    except (RuntimeError, OSError):
+        import math
+
+        return np.array([math.lgamma(k + 1.0) for k in range(n + 1)], dtype=np.float64)
+
+
 def make_value_table(n_cases: int, n_ctrls: int) -> np.ndarray:
     """float64[(n_cases+1)][(n_ctrls+1)]: -log(two-sided hypergeometric p) (R/Utils.R:137-159).
 
-    For every total i the distribution of cases among i carriers is hypergeometric; the two-sided p of an outcome is
-    the sum of all probabilities <= its own; infinities are replaced by (max finite + 1).  Computed with log-gamma in
-    float64; it need not match R's dhyper to the last ulp because oracle and GPU consume the same table.
+    For every total i the number of cases among i carriers is hypergeometric; the two-sided p of an outcome is the sum of
+    all probabilities <= its own; infinities are replaced by (max finite + 1).  Log-probabilities come from a
+    log-factorial table (math.lgamma) and the "<= own" selection is made on the log-probabilities, in the same
+    association order as the device generator (csrc/value_table.cuh), so both select identical sets; they differ only in
+    exp() rounding and summation order (~1e-15).  The table need not match R's dhyper to the last ulp: oracle and GPU
+    consume the same table.
     """
-    from scipy.special import gammaln
-
     n = n_cases + n_ctrls
+    lf = log_factorials(n)
     table = np.full((n_cases + 1, n_ctrls + 1), np.nan)
-
-    def lchoose(a, b):
-        return gammaln(a + 1.0) - gammaln(b + 1.0) - gammaln(a - b + 1.0)
-
     for i in range(n + 1):
         lo, hi = max(0, i - n_ctrls), min(i, n_cases)
         x = np.arange(lo, hi + 1)
-        logp = lchoose(n_cases, x) + lchoose(n_ctrls, i - x) - lchoose(n, i)
-        p = np.exp(logp)
-        order = np.argsort(p, kind="stable")
-        ps = p[order]
-        csum = np.cumsum(ps)
-        # sum of all probabilities <= own (ties included): index of the last element equal to own
-        last = np.searchsorted(ps, ps, side="right") - 1
-        two = np.empty_like(p)
+        a = (lf[n_cases] - lf[x]) - lf[n_cases - x]
+        b = (lf[n_ctrls] - lf[i - x]) - lf[n_ctrls - (i - x)]
+        c = (lf[n] - lf[i]) - lf[n - i]
+        logp = (a + b) - c
+        order = np.argsort(logp, kind="stable")
+        ls = logp[order]
+        csum = np.cumsum(np.exp(ls))
+        last = np.searchsorted(ls, ls, side="right") - 1  # last sorted position with a log-probability <= own
+        two = np.empty_like(logp)
         two[order] = csum[last]
         with np.errstate(divide="ignore"):
             table[x, i - x] = -np.log(two)

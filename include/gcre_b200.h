@@ -104,6 +104,15 @@ int gcre_exec_set_stream(gcre_exec* ex, void* cuda_stream);
  * Entries outside the supplied table read as -1.0, as in the reference's (n+1)x(n+1) padding. */
 int gcre_exec_set_value_table(gcre_exec* ex, const double* table, int rows, int cols);
 
+/* getValuesTable(nCases, nControls) (R/Utils.R:137-159) computed on the device for this exec's own case/control counts:
+ * vt[x][y] = -log(two-sided hypergeometric p of x cases among x + y carriers), infinities -> max finite + 1.  The R version
+ * is O(n * range^2) and infeasible for n >= 50,000.  gcre_exec_get_value_table copies the table in use to the host. */
+int gcre_exec_generate_value_table(gcre_exec* ex);
+/* log(k!) for k = 0..n (n + 1 doubles, host only): the table the generator starts from (lets a host-side check make the
+ * same decisions at exactly tied probabilities). */
+int gcre_log_factorial_table(int n, double* out);
+int gcre_exec_get_value_table(const gcre_exec* ex, double* out, int rows, int cols);
+
 /* JoinExec::setPermutedCases(const vec2d_i&)  (src/join_base.cpp:85-125).  Row-major rows x cols int32,
  * 1 = label kept, anything else = flipped; rows reused cyclically if rows < iters, surplus rows ignored. */
 int gcre_exec_set_permuted_cases_i32(gcre_exec* ex, const int32_t* perm, int rows, int cols);

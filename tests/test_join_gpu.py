@@ -185,3 +185,24 @@ def test_topk_launch_plan_paths(engine, oracles, method, kernel, monkeypatch):
     for lvl in want:
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
     assert got["4"].info["launches"] >= 3
+
+
+@pytest.mark.parametrize("nc,nt", [(2, 2), (100, 100), (57, 131), (700, 300), (5000, 5000)])
+def test_device_value_table_matches_host_restatement(engine, nc, nt):
+    """getValuesTable (R/Utils.R:137-159) generated on the device vs the numpy restatement.
+
+    Floating point: the stated tolerance is 1e-10 relative (plus 1e-9 absolute for entries that are -log(1 +- rounding)):
+    both sides select the same probability sets (comparison on bit-identical log-probabilities) and differ only in exp()
+    rounding and summation order."""
+    ex = engine.JoinExec("method1", nc, nt, 1)
+    ex.generateValueTable()
+    got = ex.getValueTable()
+    want = synth.make_value_table(nc, nt)
+    assert got.shape == want.shape
+    assert np.isfinite(got).all()
+    # entries above ~700 are -log of sums in the denormal range (p < 1e-304), where exp() has no relative accuracy on
+    # either side (and R's dhyper neither); they only have to be "astronomically significant" on both sides
+    normal = want <= 700.0
+    np.testing.assert_allclose(got[normal], want[normal], rtol=1e-10, atol=1e-9)
+    assert (got[~normal] > 700.0).all()
+    assert abs(got.max() - want.max()) <= 1.0 + 1e-9
