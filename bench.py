@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--shard", default="perms", choices=["perms", "rows"],
                     help="N > 1: 'perms' = every GPU scores all pairs against its own block of n_perms permutations (weak scaling, "
                          "results concatenated); 'rows' = the last level's upstream rows are split, maxima merged with one NCCL allreduce(max)")
+    ap.add_argument("--table", default="auto", choices=["auto", "host", "device"],
+                    help="value table: numpy on the host and uploaded (what R does), or generated on the device (needed for n >= 50k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per method for the baseline sample")
@@ -66,14 +68,18 @@ def make_workload(a):
     from geneticscre_b200 import synth
 
     t = time.time()
-    w = synth.make_workload(a.n_cases, a.n_ctrls, a.n_genes, a.n_edges, a.n_perms, a.seed, max_path_length=a.path_length, real_table=True)
+    host_table = a.table == "host" or (a.table == "auto" and a.n_cases + a.n_ctrls <= 20000)
+    w = synth.make_workload(a.n_cases, a.n_ctrls, a.n_genes, a.n_edges, a.n_perms, a.seed, max_path_length=a.path_length, real_table=True,
+                            host_table=host_table)
     return w, time.time() - t
 
 
 def workload_config(a, w):
     lv = w.net.levels
     return {
-        "workload": "BASELINE config 3: synthetic cohort, methods 1+2, full level schedule 1a,1b,2,3,4 per method",
+        "workload": ("BASELINE config 3" if (w.n_patients, a.n_genes, a.path_length, a.n_perms) == (10000, 15000, 4, 1000) else "custom") +
+                    ": synthetic cohort, methods 1+2, full level schedule 1a,1b,2,3,4" + (",5" if a.path_length >= 5 else "") + " per method",
+        "value_table": "host numpy, uploaded" if w.value_table is not None else "generated on the device",
         "patients": w.n_patients, "cases": w.n_cases, "genes_in_network": w.net.n_genes, "genes_requested": a.n_genes,
         "edges": int(w.net.edges_src.shape[0]), "path_length": a.path_length, "permutations": a.n_perms, "top_k": a.top_k,
         "pairs_per_level": {k: lv[k].n_pairs for k in lv}, "words_per_row_m1": (w.n_patients + 63) // 64,
@@ -294,7 +300,10 @@ def main():
         ex.set_stream(stream.cuda_stream)
         ex.kernel = kernel
         ex.top_k = a.top_k
-        ex.setValueTable(w.value_table)
+        if w.value_table is None:
+            ex.generateValueTable()
+        else:
+            ex.setValueTable(w.value_table)
         ex.setPermutedMasks(w.perm_masks)
         d1 = ex.createPathSet(w.gene_bits.shape[0])
         d1.load_bits(w.gene_bits)
@@ -435,7 +444,9 @@ def main():
 
     # ---- end-to-end through the reference-facing calls with HOST buffers (R-facing int matrices), N GPUs ----
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and w.value_table is None:
+        sys.stderr.write("[bench] e2e skipped: no host value table at this size (generated on the device)\n")
+    if not a.no_e2e and w.value_table is not None:
         data1_i = torch.from_numpy(synth.unpack_bits(w.gene_bits, n)).pin_memory().numpy()
         data2_i = torch.from_numpy(synth.unpack_bits(w.gene_bits2, n)).pin_memory().numpy()
         bits = np.unpackbits(w.perm_masks.view(np.uint8), axis=1, bitorder="little")[:, :n].astype(bool)
@@ -485,7 +496,7 @@ def main():
                "note": "host IntegerMatrix data + CaseORControl int matrix + f64 value table + join indices uploaded every step (pinned), per method"}
 
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and w.value_table is not None:
         try:
             cpu = ReferenceArm(w, a).sample(a.cpu_seconds)
         except Exception as e:  # the GPU numbers stand on their own

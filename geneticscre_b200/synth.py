@@ -305,12 +305,15 @@ class Workload:
 
 
 def make_workload(n_cases: int, n_ctrls: int, n_genes: int, n_edges: int, n_perms: int, seed: int,
-                  max_path_length: int = 5, real_table: bool = True, max_freq: float = 0.05, zero_frac: float = 0.6) -> Workload:
+                  max_path_length: int = 5, real_table: bool = True, max_freq: float = 0.05, zero_frac: float = 0.6,
+                  host_table: bool = True) -> Workload:
+    """``host_table=False`` leaves ``value_table`` as None: the caller generates it on the device
+    (``JoinExec.generateValueTable``), which is the only practical way for n >= 50,000."""
     n = n_cases + n_ctrls
     net = make_network(n_genes, n_edges, seed + 1, max_path_length=max_path_length)
     bits_all = make_cohort_bits(n, n_genes, seed + 2, max_freq=max_freq, zero_frac=zero_frac)
     bits = np.ascontiguousarray(bits_all[net.used_genes])
     bits2 = np.ascontiguousarray(bits[net.ents2])
     masks = make_perm_masks(n_cases, n_ctrls, n_perms, seed + 3)
-    table = make_value_table(n_cases, n_ctrls) if real_table else make_test_table(n_cases, n_ctrls, seed + 4)
+    table = None if not host_table else (make_value_table(n_cases, n_ctrls) if real_table else make_test_table(n_cases, n_ctrls, seed + 4))
     return Workload(n_cases, n_ctrls, n_perms, bits, bits2, masks, table, net)
