@@ -166,14 +166,14 @@ template <int M, bool KEEP>
 __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_sparse_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse;
   __shared__ uint32_t s_base[WARPS][M][16][32];          // base counts per warp / half / packed register / lane
-  __shared__ __align__(16) uint16_t s_queue[WARPS][QCAP];  // carriers of the current partner that survive the filter
+  __shared__ __align__(16) uint32_t s_queue[WARPS][QCAP];  // row offsets (carrier * Iw) of the partner's carriers that survive the filter
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Wp = a.Wp, Iw = a.Iw;  // Iw: words per patient row of pt (a multiple of 32: every lane owns a valid word)
   const int row_words = Wp * M;
   const unsigned long long n_work = s.n_units * (unsigned long long)s.n_perm_blocks;
   const unsigned lt_mask = (1u << lane) - 1u;
-  uint16_t* queue = s_queue[warp];
+  uint32_t* queue = s_queue[warp];
 
   float best[32];
 #pragma unroll
@@ -235,6 +235,25 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       }
     };
 
+    // the same for eight pre-multiplied row offsets (filtered partner carriers, multiplied once per lane in the filter)
+    auto add8_off = [&](uint32_t (&c16)[16], const uint4 lo, const uint4 hi) {
+      uint32_t x[8];
+      x[0] = __ldg(pt_lane + lo.x);
+      x[1] = __ldg(pt_lane + lo.y);
+      x[2] = __ldg(pt_lane + lo.z);
+      x[3] = __ldg(pt_lane + lo.w);
+      x[4] = __ldg(pt_lane + hi.x);
+      x[5] = __ldg(pt_lane + hi.y);
+      x[6] = __ldg(pt_lane + hi.z);
+      x[7] = __ldg(pt_lane + hi.w);
+      hs8(pl, x);
+      inbatch += 8;
+      if (inbatch > FLUSH_AT) {
+        flush_planes(c16, pl, 8);
+        inbatch = 0;
+      }
+    };
+
     // ---- base: the upstream row's own carriers ----
     uint32_t t0[M], nc0[M];
 #pragma unroll
@@ -285,14 +304,15 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           const bool keep = valid && !((w0 >> (c & 63)) & 1ull);   // not already a carrier of the upstream row
           const unsigned km = __ballot_sync(0xffffffffu, keep);
           ncn[h] += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
-          if (keep) queue[qn + __popc(km & lt_mask)] = (uint16_t)c;
+          if (keep) queue[qn + __popc(km & lt_mask)] = c * (uint32_t)Iw;
           qn += __popc(km);
           if (qn >= 64) {  // drain eight groups, move the remainder (< 32 entries) to the front
             __syncwarp();
 #pragma unroll 1
-            for (int gq = 0; gq < 8; gq++) add8(c16[h], *reinterpret_cast<const uint4*>(queue + gq * 8));
+            for (int gq = 0; gq < 8; gq++)
+              add8_off(c16[h], *reinterpret_cast<const uint4*>(queue + gq * 8), *reinterpret_cast<const uint4*>(queue + gq * 8 + 4));
             const uint32_t rem = qn - 64;
-            const uint16_t keepv = (lane < rem) ? queue[64 + lane] : (uint16_t)0;
+            const uint32_t keepv = (lane < rem) ? queue[64 + lane] : 0u;
             __syncwarp();
             if (lane < rem) queue[lane] = keepv;
             nd[h] += 64;
@@ -303,9 +323,10 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
         if (qn > 0) {
           // pad to a multiple of 8 with the zero row and drain
           const uint32_t padded = (qn + 7u) & ~7u;
-          if (lane < padded - qn) queue[qn + lane] = (uint16_t)s.n;
+          if (lane < padded - qn) queue[qn + lane] = (uint32_t)s.n * (uint32_t)Iw;
           __syncwarp();
-          for (uint32_t gq = 0; gq < padded / 8; gq++) add8(c16[h], *reinterpret_cast<const uint4*>(queue + gq * 8));
+          for (uint32_t gq = 0; gq < padded / 8; gq++)
+            add8_off(c16[h], *reinterpret_cast<const uint4*>(queue + gq * 8), *reinterpret_cast<const uint4*>(queue + gq * 8 + 4));
           __syncwarp();
         }
         if (inbatch > 0) {

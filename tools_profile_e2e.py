@@ -5,7 +5,7 @@ import numpy as np, torch
 from geneticscre_b200 import api, synth, _lib
 import bench
 class A: pass
-a = A(); a.__dict__.update(bench.WORKLOAD)
+a = A(); a.__dict__.update(bench.WORKLOAD); a.table = "auto"
 w, _ = bench.make_workload(a)
 lv = w.net.levels; n = w.n_patients
 def T(label, t0):
