@@ -139,18 +139,24 @@ __device__ __forceinline__ void hs8(uint32_t (&pl)[8], const uint32_t (&x)[8]) {
 // planes -> per-permutation counts, added into 16 registers of packed u16 pairs.
 // bit b of the lane's word (permutation b of the lane's 32): s = b & 7, q = b >> 3 -> register 2s + (q >> 1), half q & 1.
 __device__ __forceinline__ void flush_planes(uint32_t (&c16)[16], uint32_t (&pl)[8], int nbits) {
+  uint32_t r8[8];
+#pragma unroll
+  for (int s = 0; s < 8; s++) r8[s] = 0;
+  // plane-major with a warp-uniform early exit: only the planes a batch of `nbits` bits can populate cost instructions
+  // (as predicated code every plane was paid for: 11 % of the kernel's issue slots, profiles/r1_sparse_m1_level4_hotlines.txt)
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (j >= nbits) break;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const uint32_t v = (s >= j) ? (pl[j] >> (s - j)) : (pl[j] << (j - s));
+      r8[s] |= v & (0x01010101u << j);
+    }
+  }
 #pragma unroll
   for (int s = 0; s < 8; s++) {
-    uint32_t r8 = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      if (j < nbits) {
-        const uint32_t v = (s >= j) ? (pl[j] >> (s - j)) : (pl[j] << (j - s));
-        r8 |= v & (0x01010101u << j);
-      }
-    }
-    c16[2 * s] += __byte_perm(r8, 0u, 0x4140);
-    c16[2 * s + 1] += __byte_perm(r8, 0u, 0x4342);
+    c16[2 * s] += __byte_perm(r8[s], 0u, 0x4140);
+    c16[2 * s + 1] += __byte_perm(r8[s], 0u, 0x4342);
   }
 #pragma unroll
   for (int j = 0; j < 8; j++) pl[j] = 0;
