@@ -222,7 +222,7 @@ struct gcre_uidset {
   uint32_t n_uids = 0, n_signs = 0;
   unsigned long long total = 0, max_loc_end = 0, max_res_end = 0;
   std::vector<unsigned long long> h_prefix, h_units;  // [U+1] running sums of count and of ceil(count / PB)
-  DevBuf count, loc, prefix, res, units, signs;
+  DevBuf count, loc, prefix, res, units, unit_idx, signs;
 };
 
 static void drop_view(gcre_pathset* ps) {
@@ -862,7 +862,7 @@ static int launch_join_dense(gcre_exec* ex, const JoinParams& jp, bool keep, int
 static int build_uidset(gcre_exec* ex, int path_length, const gcre_uid_ref* uids, uint32_t n_uids, const int32_t* signs, uint32_t n_signs,
                         gcre_uidset* us) {
   us->ex = ex;
-  for (DevBuf* b : {&us->count, &us->loc, &us->prefix, &us->res, &us->units, &us->signs}) b->owner = ex;
+  for (DevBuf* b : {&us->count, &us->loc, &us->prefix, &us->res, &us->units, &us->unit_idx, &us->signs}) b->owner = ex;
   us->path_length = path_length;
   us->n_uids = n_uids;
   us->n_signs = n_signs;
@@ -902,6 +902,19 @@ static int build_uidset(gcre_exec* ex, int path_length, const gcre_uid_ref* uids
   CKS(up(us->res, h_res.data(), (size_t)n_uids * 8));
   CKS(up(us->prefix, us->h_prefix.data(), ((size_t)n_uids + 1) * 8));
   CKS(up(us->units, us->h_units.data(), ((size_t)n_uids + 1) * 8));
+  {
+    // upstream row of every unit (units of one row are consecutive)
+    std::vector<uint32_t>& h_uidx = ex->h_loc;  // h_loc was uploaded above and the copy is stream-ordered: safe to reuse after a sync
+    CK(cudaStreamSynchronize(ex->stream));
+    if (nu > 0xfffffff0ull) return fail(GCRE_ERR_ARG, "join too large: more than 2^32 work units");
+    h_uidx.resize((size_t)nu);
+    size_t pos = 0;
+    for (uint32_t u = 0; u < n_uids; u++) {
+      const size_t k = (size_t)(us->h_units[u + 1] - us->h_units[u]);
+      for (size_t q = 0; q < k; q++) h_uidx[pos++] = u;
+    }
+    CKS(up(us->unit_idx, h_uidx.data(), (size_t)nu * 4));
+  }
   CKS(up(us->signs, signs, (size_t)n_signs * 4));
   CK(cudaStreamSynchronize(ex->stream));  // the staging vectors are reused by the next index
   return GCRE_OK;
@@ -913,6 +926,7 @@ static void free_uidset_buffers(gcre_uidset* us) {
   us->prefix.release();
   us->res.release();
   us->units.release();
+  us->unit_idx.release();
   us->signs.release();
 }
 
@@ -1029,6 +1043,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     sp.off1 = paths1->view.off; sp.len1 = paths1->view.len; sp.car1 = paths1->view.car; sp.ncase1 = paths1->view.ncase;
     sp.n = ex->n;
     sp.unit_prefix = (const unsigned long long*)us->units.p;
+    sp.unit_idx = (const uint32_t*)us->unit_idx.p;
     sp.work_counter = (unsigned long long*)(ex->d_scalars + 2);
     sp.n_perm_blocks = ex->Iw / 32;
   }

@@ -53,6 +53,7 @@ struct SparseParams {
   const uint32_t* off1; const uint32_t* len1; const uint16_t* car1; const uint32_t* ncase1;
   int n;                                  // patients; also the sentinel carrier index (zero row of pt)
   const unsigned long long* unit_prefix;  // [U+1] running sum of ceil(count/PB)
+  const uint32_t* unit_idx;               // [n_units_total] upstream row of every unit (replaces a binary search per unit)
   unsigned long long unit_begin, n_units;  // units of this launch
   unsigned long long* work_counter;
   int n_perm_blocks;                      // ceil(Iw / 32)
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       pb_cur = pb;
     }
     const bool first_pb = (pb == 0);
-    const uint32_t idx = find_uid(s.unit_prefix, a.n_uids, unit);
+    const uint32_t idx = s.unit_idx[unit];
     const uint32_t sub = (uint32_t)(unit - s.unit_prefix[idx]);
     const uint32_t cnt_idx = (uint32_t)a.count[idx];
     const uint32_t j0 = sub * PB, j1 = min(cnt_idx, j0 + PB);
@@ -306,8 +307,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           const uint32_t i = i0 + lane;
           const bool valid = i < len;
           const uint32_t c = valid ? s.car1[o + i] : 0u;
-          const uint64_t w0 = valid ? __ldg(p0h + (c >> 6)) : 0ull;
-          const bool keep = valid && !((w0 >> (c & 63)) & 1ull);   // not already a carrier of the upstream row
+          const uint32_t w0 = valid ? __ldg(reinterpret_cast<const uint32_t*>(p0h) + (c >> 5)) : 0u;
+          const bool keep = valid && !((w0 >> (c & 31)) & 1u);   // not already a carrier of the upstream row
           const unsigned km = __ballot_sync(0xffffffffu, keep);
           ncn[h] += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
           if (keep) queue[qn + __popc(km & lt_mask)] = c * (uint32_t)Iw;
