@@ -206,3 +206,33 @@ def test_device_value_table_matches_host_restatement(engine, nc, nt):
     np.testing.assert_allclose(got[normal], want[normal], rtol=1e-10, atol=1e-9)
     assert (got[~normal] > 700.0).all()
     assert abs(got.max() - want.max()) <= 1.0 + 1e-9
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_many_permutations_span_several_blocks(engine, oracles, method, kernel):
+    """More than 1,024 permutations: the sparse kernel walks several 1,024-permutation blocks per unit (maxima flushed
+    between blocks, true scores / kept rows only on the first), the dense kernel many 128-permutation tiles."""
+    w = synth.make_workload(40, 45, 60, 170, 2100, seed=404, max_path_length=4, real_table=True, max_freq=0.15, zero_frac=0.2)
+    want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, 6)
+    got, kept, _ = run_engine(engine, w, method, 4, 6, kernel)
+    for k in kept_want:
+        assert np.array_equal(kept[k], kept_want[k])
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_dense_carrier_rows(engine, oracles, method, kernel):
+    """Common variants (up to half of the patients carry each gene): partner deltas of several hundred carriers exercise
+    the plane-batch overflow (> 248 carriers between flushes) and the carrier-queue drain of the sparse kernel."""
+    w = synth.make_workload(600, 630, 40, 110, 300, seed=505, max_path_length=4, real_table=True, max_freq=0.5, zero_frac=0.0)
+    assert np.unpackbits(w.gene_bits.view(np.uint8), axis=1).sum(axis=1).max() > 400
+    want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, 6)
+    got, kept, _ = run_engine(engine, w, method, 4, 6, kernel)
+    for k in kept_want:
+        assert np.array_equal(kept[k], kept_want[k])
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
+        assert got[lvl].info["kernel"] == kernel
