@@ -19,8 +19,8 @@ in the checkout; sizes generated are reported in `config`).  One step = the whol
 
 Multi-GPU (N > 1), one process per GPU:
   --shard perms (default)  every GPU scores ALL pairs against its own block of n_perms permutations (the decomposition of
-             BASELINE config 4/5: more permutations, same cohort); per-permutation maxima are concatenated with one
-             all-gather, top-K is identical on every rank.  Per-GPU work is fixed => "scaling": "weak"; value counts
+             BASELINE config 4/5: more permutations, same cohort); the per-permutation maxima are merged with ONE NCCL
+             allreduce(max) over the N x n_perms vector (each rank fills its block), top-K is identical on every rank.  Per-GPU work is fixed => "scaling": "weak"; value counts
              N x n_perms permutations.
   --shard rows             the last level's upstream rows are split by pair count, levels 1-3 are computed redundantly,
              permutation maxima are merged with ONE NCCL allreduce(max) per join, top-K lists with an all-gather +
@@ -334,9 +334,11 @@ def main():
             res_set = ex.createPathSet(lv[k].n_pairs) if (keep or (k in ("2", "3") and a.path_length > int(k))) else zero
             if k == last and shard_perms:
                 r = ex.join(uid[k], prev, operand, res_set)
-                # result assembly: the per-permutation maxima of all blocks are concatenated (no reduction needed)
-                _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations))
-                dist.all_gather_into_tensor(st["perm_all"], st["perm_t"])
+                # result assembly: every rank drops its block of maxima into a zeroed N x I vector and ONE NCCL
+                # allreduce(max) over NVLink merges them (maxima are >= +0, so max against the zeros is concatenation)
+                st["perm_all"].zero_()
+                _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_all"].data_ptr() + 4 * ex.iterations * rank, ex.iterations))
+                dist.all_reduce(st["perm_all"], op=dist.ReduceOp.MAX)
             elif k == last and world > 1:
                 r = ex.join(uid[k], prev, operand, zero, uid_range=my_shard, skip_host_perm=True)
                 _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations))
@@ -518,7 +520,7 @@ def main():
         cfg = workload_config(a, w)
         cfg["permutations_total"] = w.n_perms * (world if shard_perms else 1)
         cfg["parallelism"] = ("1 GPU" if world == 1 else
-                              f"{world} GPUs, one block of {w.n_perms} permutations per GPU over all pairs; maxima concatenated (all-gather)" if shard_perms else
+                              f"{world} GPUs, one block of {w.n_perms} permutations per GPU over all pairs; maxima merged with one NCCL allreduce(max)" if shard_perms else
                               f"{world} GPUs, level-{last} upstream rows sharded by pair count; one NCCL allreduce(max) per join + top-K gather")
         line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (shard_perms or world == 1) else "strong", "vs_baseline": None,
