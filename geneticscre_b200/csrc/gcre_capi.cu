@@ -825,10 +825,15 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
     CK(cudaStreamSynchronize(ex->stream));
   }
   ps->view.total = total;
-  CK(dev_alloc(ex, (void**)&ps->view.car, std::max<size_t>(total, 8) * 2));
+  const bool wide = sparse_wide(ex->n);
+  CK(dev_alloc(ex, (void**)&ps->view.car, std::max<size_t>(total, 8) * (wide ? 4 : 2)));
   if (items > 0) {
-    build_lists_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ex->n, ps->view.off, ps->view.car,
-                                                                         ps->view.ncase);
+    if (wide)
+      build_lists_kernel<uint32_t><<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ex->n, ps->view.off,
+                                                                                     (uint32_t*)ps->view.car, ps->view.ncase);
+    else
+      build_lists_kernel<uint16_t><<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ex->n, ps->view.off,
+                                                                                     (uint16_t*)ps->view.car, ps->view.ncase);
     CK(cudaGetLastError());
     LAUNCHED();
   }
@@ -1030,9 +1035,9 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   // ---- kernel choice ----
   int kernel = opts ? opts->kernel : GCRE_KERNEL_AUTO;
   if (kernel != GCRE_KERNEL_DENSE && kernel != GCRE_KERNEL_SPARSE)
-    kernel = sparse_supported(ex->n, t_needed, ex->iters) ? GCRE_KERNEL_SPARSE : GCRE_KERNEL_DENSE;
+    kernel = sparse_supported(ex->n, t_needed, ex->iters, ex->Iw) ? GCRE_KERNEL_SPARSE : GCRE_KERNEL_DENSE;
   // an explicit request for the sparse kernel is honoured whenever its index widths allow (also with few permutations)
-  if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, 1 << 30)) kernel = GCRE_KERNEL_DENSE;
+  if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, 1 << 30, ex->Iw)) kernel = GCRE_KERNEL_DENSE;
   SparseParams sp;
   memset(&sp, 0, sizeof sp);
   if (kernel == GCRE_KERNEL_SPARSE) {

@@ -16,6 +16,8 @@
 //           max kept in registers across all units of the warp, merged at the end with one atomicMax per permutation
 //   true scores / top-K candidates / kept rows exactly as in the dense kernel.
 #pragma once
+#include <cstdlib>
+
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -42,15 +44,15 @@ constexpr int min_blocks(int m) { return m == 1 ? 8 : 4; }
 struct SparseView {
   uint32_t* off = nullptr;    // [size*M + 1]  padded prefix (entries), multiples of 8
   uint32_t* len = nullptr;    // [size*M]      true carrier counts
-  uint16_t* car = nullptr;    // [off[size*M]]
+  void* car = nullptr;        // [off[size*M]] patient indices: u16 when n <= 65,535, else u32
   uint32_t* ncase = nullptr;  // [size*M] carriers < n_cases (a prefix of the ascending list)
   size_t total = 0;           // padded entries
   bool valid = false;
 };
 
 struct SparseParams {
-  const uint32_t* off0; const uint32_t* len0; const uint16_t* car0; const uint32_t* ncase0;
-  const uint32_t* off1; const uint32_t* len1; const uint16_t* car1; const uint32_t* ncase1;
+  const uint32_t* off0; const uint32_t* len0; const void* car0; const uint32_t* ncase0;   // car: CT[] (u16 or u32)
+  const uint32_t* off1; const uint32_t* len1; const void* car1; const uint32_t* ncase1;
   int n;                                  // patients; also the sentinel carrier index (zero row of pt)
   const unsigned long long* unit_prefix;  // [U+1] running sum of ceil(count/PB)
   const uint32_t* unit_idx;               // [n_units_total] upstream row of every unit (replaces a binary search per unit)
@@ -76,8 +78,9 @@ __global__ void half_popcount_kernel(const uint64_t* __restrict__ rows, long lon
   }
 }
 
+template <typename CT>
 __global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, int n_cases, int sentinel,
-                                   const uint32_t* __restrict__ off, uint16_t* __restrict__ car, uint32_t* __restrict__ ncase) {
+                                   const uint32_t* __restrict__ off, CT* __restrict__ car, uint32_t* __restrict__ ncase) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= n_items) return;
@@ -100,14 +103,14 @@ __global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long 
       const int b = __ffsll((long long)w) - 1;
       w &= w - 1;
       const int patient = k * 64 + b;
-      car[o++] = (uint16_t)patient;
+      car[o++] = (CT)patient;
       nc += patient < n_cases;
     }
     pos += __shfl_sync(0xffffffffu, incl, 31);
   }
   // pad with the sentinel up to the next list start
   const uint32_t end = off[warp + 1];
-  for (uint32_t o = pos + lane; o < end; o += 32) car[o] = (uint16_t)sentinel;
+  for (uint32_t o = pos + lane; o < end; o += 32) car[o] = (CT)sentinel;
   nc = __reduce_add_sync(0xffffffffu, nc);
   if (lane == 0) ncase[warp] = nc;
 }
@@ -169,9 +172,23 @@ __device__ __forceinline__ int bits_for(int count) { return 32 - __clz(count); }
 #define GCRE_C16_REG(b) (2 * ((b) & 7) + ((b) >> 4))
 #define GCRE_C16_HI(b) (((b) >> 3) & 1)
 
-template <int M, bool KEEP>
+// eight consecutive carriers of a (16-byte aligned, padded) list -> eight patient indices
+__device__ __forceinline__ void load8(const uint16_t* p, uint32_t (&c)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  c[0] = v.x & 0xffffu; c[1] = v.x >> 16; c[2] = v.y & 0xffffu; c[3] = v.y >> 16;
+  c[4] = v.z & 0xffffu; c[5] = v.z >> 16; c[6] = v.w & 0xffffu; c[7] = v.w >> 16;
+}
+__device__ __forceinline__ void load8(const uint32_t* p, uint32_t (&c)[8]) {
+  const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
+}
+
+// CT = carrier index type of the list views: uint16_t (n <= 65,535) or uint32_t
+template <int M, bool KEEP, typename CT>
 __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_sparse_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse;
+  const CT* car0 = static_cast<const CT*>(s.car0);
+  const CT* car1 = static_cast<const CT*>(s.car1);
   __shared__ uint32_t s_base[WARPS][M][16][32];          // base counts per warp / half / packed register / lane
   __shared__ __align__(16) uint32_t s_queue[WARPS][QCAP];  // row offsets (carrier * Iw) of the partner's carriers that survive the filter
 
@@ -223,17 +240,12 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     for (int j = 0; j < 8; j++) pl[j] = 0;
     int inbatch = 0;
 
-    // add the eight carriers packed in v (u16 x 8; sentinel entries hit the zero row) to the bit planes
-    auto add8 = [&](uint32_t (&c16)[16], const uint4 v) {
-      uint32_t x[8];
-      x[0] = __ldg(pt_lane + (v.x & 0xffffu) * Iw);
-      x[1] = __ldg(pt_lane + (v.x >> 16) * Iw);
-      x[2] = __ldg(pt_lane + (v.y & 0xffffu) * Iw);
-      x[3] = __ldg(pt_lane + (v.y >> 16) * Iw);
-      x[4] = __ldg(pt_lane + (v.z & 0xffffu) * Iw);
-      x[5] = __ldg(pt_lane + (v.z >> 16) * Iw);
-      x[6] = __ldg(pt_lane + (v.w & 0xffffu) * Iw);
-      x[7] = __ldg(pt_lane + (v.w >> 16) * Iw);
+    // add eight carriers of a list (sentinel entries hit the zero row) to the bit planes
+    auto add8 = [&](uint32_t (&c16)[16], const CT* lst8) {
+      uint32_t c[8], x[8];
+      load8(lst8, c);
+#pragma unroll
+      for (int q = 0; q < 8; q++) x[q] = __ldg(pt_lane + c[q] * (uint32_t)Iw);
       hs8(pl, x);
       inbatch += 8;
       if (inbatch > FLUSH_AT) {
@@ -272,8 +284,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       const uint32_t o = s.off0[item], plen = s.off0[item + 1] - o;
       t0[h] = s.len0[item];
       nc0[h] = s.ncase0[item];
-      const uint4* lst = reinterpret_cast<const uint4*>(s.car0 + o);
-      for (uint32_t i = 0; i < plen / 8; i++) add8(acc, __ldg(lst + i));
+      for (uint32_t i = 0; i < plen; i += 8) add8(acc, car0 + o + i);
       if (inbatch > 0) {
         flush_planes(acc, pl, bits_for(inbatch));
         inbatch = 0;
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
         for (uint32_t i0 = 0; i0 < len; i0 += 32) {
           const uint32_t i = i0 + lane;
           const bool valid = i < len;
-          const uint32_t c = valid ? s.car1[o + i] : 0u;
+          const uint32_t c = valid ? (uint32_t)car1[o + i] : 0u;
           const uint32_t w0 = valid ? __ldg(reinterpret_cast<const uint32_t*>(p0h) + (c >> 5)) : 0u;
           const bool keep = valid && !((w0 >> (c & 31)) & 1u);   // not already a carrier of the upstream row
           const unsigned km = __ballot_sync(0xffffffffu, keep);
@@ -424,9 +435,20 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
   if (pb_cur >= 0) flush_best(pb_cur);
 }
 
-static inline bool sparse_supported(int n, long long t_needed, int iters) {
-  // u16 carrier indices and u16 packed counters; lanes map to permutation words, so few permutations waste lanes
-  return n <= 65535 && t_needed <= 65535 && iters > 256;   // n itself is the sentinel carrier index (must fit u16)
+// u32 carrier indices when n (which is also the sentinel index) does not fit u16; GCRE_TEST_WIDE_CARRIERS=1 (test hook)
+// forces the u32 path on small cohorts
+static inline bool sparse_wide(int n) { return n > 65535 || std::getenv("GCRE_TEST_WIDE_CARRIERS") != nullptr; }
+
+static inline bool sparse_supported(int n, long long t_needed, int iters, int Iw) {
+  // packed u16 counters; 32-bit row offsets into the patient-major masks; lanes map to permutation words, so few
+  // permutations waste lanes
+  return t_needed <= 65535 && iters > 256 && ((unsigned long long)n + 1) * (unsigned long long)Iw < 0xffffffffull;
+}
+
+template <int M, bool KEEP>
+static inline void launch_sparse_ct(unsigned grid, cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, bool wide) {
+  if (wide) join_sparse_kernel<M, KEEP, uint32_t><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+  else join_sparse_kernel<M, KEEP, uint16_t><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
 }
 
 static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count) {
@@ -434,12 +456,13 @@ static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinPara
   if (n_work == 0) return cudaSuccess;
   const unsigned long long want = (n_work + sparse::WARPS - 1) / sparse::WARPS;
   const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * sparse::min_blocks(M));
+  const bool wide = sparse_wide(sp.n);
   if (M == 1) {
-    if (keep) join_sparse_kernel<1, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
-    else join_sparse_kernel<1, false><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+    if (keep) launch_sparse_ct<1, true>(grid, stream, jp, sp, wide);
+    else launch_sparse_ct<1, false>(grid, stream, jp, sp, wide);
   } else {
-    if (keep) join_sparse_kernel<2, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
-    else join_sparse_kernel<2, false><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+    if (keep) launch_sparse_ct<2, true>(grid, stream, jp, sp, wide);
+    else launch_sparse_ct<2, false>(grid, stream, jp, sp, wide);
   }
   return cudaGetLastError();
 }

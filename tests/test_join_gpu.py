@@ -236,3 +236,18 @@ def test_dense_carrier_rows(engine, oracles, method, kernel):
     for lvl in want:
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
         assert got[lvl].info["kernel"] == kernel
+
+
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_wide_carrier_indices(engine, oracles, method, monkeypatch):
+    """Cohorts above 65,535 patients use 32-bit carrier indices in the sparse kernel's lists; GCRE_TEST_WIDE_CARRIERS
+    forces that code path on a cohort the oracle can check."""
+    monkeypatch.setenv("GCRE_TEST_WIDE_CARRIERS", "1")
+    w = synth.make_workload(300, 310, 120, 400, 300, seed=606, max_path_length=5, real_table=True, max_freq=0.3, zero_frac=0.2)
+    want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 5, 7)
+    got, kept, _ = run_engine(engine, w, method, 5, 7, _lib.KERNEL_SPARSE)
+    for k in kept_want:
+        assert np.array_equal(kept[k], kept_want[k])
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
+        assert got[lvl].info["kernel"] == _lib.KERNEL_SPARSE
