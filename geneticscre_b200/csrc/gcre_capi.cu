@@ -1035,9 +1035,9 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   // ---- kernel choice ----
   int kernel = opts ? opts->kernel : GCRE_KERNEL_AUTO;
   if (kernel != GCRE_KERNEL_DENSE && kernel != GCRE_KERNEL_SPARSE)
-    kernel = sparse_supported(ex->n, t_needed, ex->iters, ex->Iw) ? GCRE_KERNEL_SPARSE : GCRE_KERNEL_DENSE;
-  // an explicit request for the sparse kernel is honoured whenever its index widths allow (also with few permutations)
-  if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, 1 << 30, ex->Iw)) kernel = GCRE_KERNEL_DENSE;
+    kernel = (sparse_supported(ex->n, t_needed, ex->Iw) && sparse_preferred(ex->W64, ex->Ip, ex->Iw)) ? GCRE_KERNEL_SPARSE : GCRE_KERNEL_DENSE;
+  // an explicit request for the sparse kernel is honoured whenever its index widths allow
+  if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, ex->Iw)) kernel = GCRE_KERNEL_DENSE;
   SparseParams sp;
   memset(&sp, 0, sizeof sp);
   if (kernel == GCRE_KERNEL_SPARSE) {

@@ -439,10 +439,17 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 // forces the u32 path on small cohorts
 static inline bool sparse_wide(int n) { return n > 65535 || std::getenv("GCRE_TEST_WIDE_CARRIERS") != nullptr; }
 
-static inline bool sparse_supported(int n, long long t_needed, int iters, int Iw) {
-  // packed u16 counters; 32-bit row offsets into the patient-major masks; lanes map to permutation words, so few
-  // permutations waste lanes
-  return t_needed <= 65535 && iters > 256 && ((unsigned long long)n + 1) * (unsigned long long)Iw < 0xffffffffull;
+// can the sparse kernel run this shape at all: packed u16 counters, 32-bit row offsets into the patient-major masks
+static inline bool sparse_supported(int n, long long t_needed, int Iw) {
+  return t_needed <= 65535 && ((unsigned long long)n + 1) * (unsigned long long)Iw < 0xffffffffull;
+}
+
+// AUTO choice.  Per pair the dense kernel issues ~ W64 * Ip * 5 / 32 warp instructions (Ip = permutations padded to its
+// 128-wide tile), the sparse kernel ~1,000 per 1,024-permutation block almost independent of W64 (measured on config 3:
+// 950 / pair, profiles/r1_sparse_m1_level4_full.txt).  Dense wins only for very short rows with few permutations
+// (the vignette: W64 = 4).  Measured at 50,000 patients / 100 permutations: dense 1.9 s per step.
+static inline bool sparse_preferred(int W64, int Ip_dense, int Iw) {
+  return (long long)W64 * Ip_dense > 6400ll * (Iw / 32);
 }
 
 template <int M, bool KEEP>
