@@ -1,6 +1,6 @@
 """Host-side timing breakdown of the e2e step and of the resident step under different stream choices (dev tool)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from geneticscre_b200 import api, synth, _lib
 import bench

@@ -1,6 +1,6 @@
 """Host-side timing breakdown of one resident schedule step (dev tool)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from geneticscre_b200 import api, synth, _lib
 import bench
