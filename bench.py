@@ -80,6 +80,7 @@ def workload_config(a, w):
         "workload": ("BASELINE config 3" if (w.n_patients, a.n_genes, a.path_length, a.n_perms) == (10000, 15000, 4, 1000) else "custom") +
                     ": synthetic cohort, methods 1+2, full level schedule 1a,1b,2,3,4" + (",5" if a.path_length >= 5 else "") + " per method",
         "value_table": "host numpy, uploaded" if w.value_table is not None else "generated on the device",
+        "arithmetic": "u64 bitsets / u16 carrier lists, u32+u16 integer counts, f64 score table (f32 copy for method-1 permutation look-ups)",
         "patients": w.n_patients, "cases": w.n_cases, "genes_in_network": w.net.n_genes, "genes_requested": a.n_genes,
         "edges": int(w.net.edges_src.shape[0]), "path_length": a.path_length, "permutations": a.n_perms, "top_k": a.top_k,
         "pairs_per_level": {k: lv[k].n_pairs for k in lv}, "words_per_row_m1": (w.n_patients + 63) // 64,
@@ -240,7 +241,7 @@ def run_reference_arm(a):
     last = vals[-1] if vals else {"cores": arm.cores, "kind": arm.kind, "sample": ""}
     ms = 1e3 * float(np.mean([v["seconds"] for v in vals])) if vals else None
     line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitsets, u32 counts, f64 scores",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "impl": "reference", "config": workload_config(a, w),
             "cpu_baseline": {"value": value, "unit": "pair*perm/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": value, "unit": "pair*perm/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -524,7 +525,7 @@ def main():
                               f"{world} GPUs, level-{last} upstream rows sharded by pair count; one NCCL allreduce(max) per join + top-K gather")
         line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (shard_perms or world == 1) else "strong", "vs_baseline": None,
-                "dtype": "u64 bitsets, u32 counts, f64 scores", "data": "synthetic", "config": cfg, "clocks": clocks,
+                "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu,
                 "pair_perm_per_step": pp_step, "workload_gen_s": round(gen_s, 1)}
         print(json.dumps(line))
