@@ -212,6 +212,8 @@ struct gcre_pathset {
   uint32_t size = 0;
   uint64_t* d_rows = nullptr;
   long long max_half_pop = 0;  // max carriers in any half-row; -1 = unknown (recomputed on demand)
+  bool zero_pending = false;   // rows are logically zero but the memset has not been issued yet (skipped altogether when
+                               // the set's first use is as the fully overwritten result of a join)
   SparseView view;             // carrier lists, built on first use by a sparse join
 };
 
@@ -221,9 +223,18 @@ struct gcre_uidset {
   int path_length = 0;
   uint32_t n_uids = 0, n_signs = 0;
   unsigned long long total = 0, max_loc_end = 0, max_res_end = 0;
+  bool res_is_prefix = true;   // every path_idx equals the running sum of counts: a full join overwrites rows [0, total)
   std::vector<unsigned long long> h_prefix, h_units;  // [U+1] running sums of count and of ceil(count / PB)
   DevBuf count, loc, prefix, res, units, unit_idx, signs;
 };
+
+static int materialize_zero(gcre_pathset* ps) {
+  if (!ps->zero_pending) return GCRE_OK;
+  ps->zero_pending = false;
+  const size_t bytes = (size_t)ps->size * ps->ex->Wp * ps->ex->M * 8;
+  if (bytes) CK(cudaMemsetAsync(ps->d_rows, 0, bytes, ps->ex->stream));
+  return GCRE_OK;
+}
 
 static void drop_view(gcre_pathset* ps) {
   dev_free(ps->ex, ps->view.off);
@@ -543,12 +554,7 @@ extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_path
       delete ps;
       return fail(GCRE_ERR_NOMEM, "device allocation of %zu bytes for a path set failed: %s", bytes, cudaGetErrorString(e));
     }
-    e = cudaMemsetAsync(ps->d_rows, 0, bytes, ex->stream);
-    if (e != cudaSuccess) {
-      dev_free(ex, ps->d_rows);
-      delete ps;
-      return fail(GCRE_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-    }
+    ps->zero_pending = true;
   }
   *out = ps;
   return GCRE_OK;
@@ -600,6 +606,7 @@ extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint
   // equal to n is always accepted (the reference throws when n is a multiple of its SIMD width: SURVEY App. D1)
   if (rows > 0 && (cols < 0 || cols > ex->W64 * 64)) return fail(GCRE_ERR_RANGE, "assertion");
   if (rows == 0) return GCRE_OK;
+  ps->zero_pending = false;
   CK(cudaMemsetAsync(ps->d_rows, 0, (size_t)ps->size * row_words(ex) * 8, ex->stream));
   const uint32_t rows_per_blk = (uint32_t)std::max<size_t>(1, ((size_t)256 << 20) / ((size_t)std::max(cols, 1) * 4));
   CKS(ex->scratch.ensure((size_t)std::min(rows_per_blk, rows) * std::max(cols, 1) * 4));
@@ -625,6 +632,7 @@ extern "C" int gcre_pathset_load_bits(gcre_pathset* ps, const uint64_t* bits, ui
   if (rows != ps->size) return fail(GCRE_ERR_ASSERT, "assertion");
   if (rows > 0 && (words_per_row < 0 || words_per_row > ex->W64)) return fail(GCRE_ERR_RANGE, "assertion");
   if (rows == 0) return GCRE_OK;
+  ps->zero_pending = false;
   CK(cudaMemsetAsync(ps->d_rows, 0, (size_t)ps->size * row_words(ex) * 8, ex->stream));
   const size_t bytes = (size_t)rows * words_per_row * 8;
   if (bytes) {
@@ -649,9 +657,11 @@ extern "C" int gcre_pathset_select(const gcre_pathset* ps, const int32_t* indice
   // src/gcre_paths.h:85: check_index(indices[k], size)
   for (uint32_t k = 0; k < n; k++)
     if (indices[k] < 0 || (uint32_t)indices[k] >= ps->size) return fail(GCRE_ERR_RANGE, "assertion");
+  CKS(materialize_zero(const_cast<gcre_pathset*>(ps)));
   gcre_pathset* res = nullptr;
   CKS(gcre_pathset_create(ex, n, &res));
   if (n) {
+    res->zero_pending = false;  // every row is written by the gather below
     int rc = [&]() -> int {
       CKS(ex->scratch.ensure((size_t)n * 4));
       CK(cudaMemcpyAsync(ex->scratch.p, indices, (size_t)n * 4, cudaMemcpyHostToDevice, ex->stream));
@@ -678,6 +688,7 @@ extern "C" int gcre_pathset_set_row(gcre_pathset* ps, uint32_t idx, const uint64
   gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
   CKS(use_device(ex));
   if (idx >= ps->size) return fail(GCRE_ERR_RANGE, "assertion");  // src/gcre_paths.h:50
+  CKS(materialize_zero(ps));
   for (int h = 0; h < ex->M; h++)
     CK(cudaMemcpyAsync(ps->d_rows + (size_t)idx * row_words(ex) + (size_t)h * ex->Wp, words + (size_t)h * ex->W64, (size_t)ex->W64 * 8,
                        cudaMemcpyHostToDevice, ex->stream));
@@ -692,6 +703,7 @@ extern "C" int gcre_pathset_get_row(const gcre_pathset* ps, uint32_t idx, uint64
   const gcre_exec* ex = ps->ex;
   CKS(use_device(ex));
   if (idx >= ps->size) return fail(GCRE_ERR_RANGE, "assertion");  // src/gcre_paths.h:45
+  CKS(materialize_zero(const_cast<gcre_pathset*>(ps)));
   for (int h = 0; h < ex->M; h++)
     CK(cudaMemcpyAsync(words + (size_t)h * ex->W64, ps->d_rows + (size_t)idx * row_words(ex) + (size_t)h * ex->Wp, (size_t)ex->W64 * 8,
                        cudaMemcpyDeviceToHost, ex->stream));
@@ -704,6 +716,7 @@ extern "C" int gcre_pathset_download(const gcre_pathset* ps, uint64_t* out) {
   gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
   CKS(use_device(ex));
   if (!ps->size) return GCRE_OK;
+  CKS(materialize_zero(const_cast<gcre_pathset*>(ps)));
   const size_t words = (size_t)ps->size * ex->W64 * ex->M;
   CKS(ex->scratch.ensure(words * 8));
   if (ex->M == 1)
@@ -801,6 +814,7 @@ extern "C" int gcre_merge_topk(const gcre_score* lists, const int* list_sizes, i
 // ------------------------------------------------------------------------------------------------------------------
 static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
   if (ps->view.valid) return GCRE_OK;
+  CKS(materialize_zero(ps));
   drop_view(ps);
   const long long items = (long long)ps->size * ex->M;
   CK(dev_alloc(ex, (void**)&ps->view.off, (size_t)(items + 1) * 4));
@@ -888,6 +902,7 @@ static int build_uidset(gcre_exec* ex, int path_length, const gcre_uid_ref* uids
     us->h_prefix[u] = total;
     us->h_units[u] = nu;
     if (c > 0) {
+      if (uids[u].path_idx != total) us->res_is_prefix = false;
       us->max_loc_end = std::max(us->max_loc_end, (unsigned long long)uids[u].location + c);
       us->max_res_end = std::max(us->max_res_end, (unsigned long long)uids[u].path_idx + c);
     }
@@ -1021,6 +1036,14 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     ue = std::min(std::max(opts->uid_end, ub), n_uids);
   }
   const unsigned long long pair_lo = h_prefix[ub], pair_hi = h_prefix[ue];
+
+  CKS(materialize_zero(const_cast<gcre_pathset*>(paths0)));
+  CKS(materialize_zero(const_cast<gcre_pathset*>(paths1)));
+  if (keep) {
+    // a full join whose result rows are the running sums of the counts overwrites every word of the result set
+    if (pair_lo == 0 && pair_hi == total && us->res_is_prefix) paths_res->zero_pending = false;
+    else CKS(materialize_zero(paths_res));
+  }
 
   tr.mark("checks");
   // ---- value-table coverage: a joined half-row has at most maxpop0 + maxpop1 carriers ----
