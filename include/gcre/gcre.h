@@ -86,12 +86,14 @@ class JoinExec {
   const int iters_requested;
 
   int top_k = 12;    // src/gcre.h:120
-  int nthreads = 0;  // accepted for compatibility; the join runs on the GPU (GCRE_DEVICE selects which)
+  int nthreads = 0;  // accepted for compatibility; the join runs on the GPU(s)
   int width_vec = 0;
 
   static Method to_method(string name) { return name == "method1" ? Method::method1 : Method::method2; }  // src/gcre.h:125-133
 
-  // src/join_base.cpp:37-59
+  // src/join_base.cpp:37-59.  GPUs: GCRE_DEVICES="0,2,3" (explicit ordinals) or GCRE_GPUS=N (ordinals 0..N-1) or
+  // GCRE_DEVICE=k (one GPU, default 0).  With several GPUs every path set is replicated, joins that keep their rows run
+  // on every GPU, and score-only joins (levels 4 and 5 - where the pairs are) are sharded over the GPUs by upstream row.
   JoinExec(string method_name, int num_cases_, int num_ctrls_, int iters)
       : method(to_method(method_name)),
         num_cases(num_cases_),
@@ -100,12 +102,22 @@ class JoinExec {
         iterations(padded_iterations(iters)),
         iters_requested(iters) {
     check_true(num_cases > 0 && num_ctrls > 0 && iters >= 0);
-    const char* dev = std::getenv("GCRE_DEVICE");
-    gcre_detail::raise(gcre_exec_create((int)method, num_cases, num_ctrls, iters, dev ? std::atoi(dev) : 0, &handle_));
+    const std::vector<int> devices = devices_from_env();
+    handles_.assign(devices.size(), nullptr);
+    try {
+      gcre_for_each_device(devices.size(), [&](size_t d) {
+        return gcre_exec_create((int)method, num_cases, num_ctrls, iters, devices[d], &handles_[d]);
+      });
+    } catch (...) {
+      for (gcre_exec* h : handles_) gcre_exec_destroy(h);
+      throw;
+    }
   }
   JoinExec(const JoinExec&) = delete;
   JoinExec& operator=(const JoinExec&) = delete;
-  ~JoinExec() { gcre_exec_destroy(handle_); }
+  ~JoinExec() {
+    for (gcre_exec* h : handles_) gcre_exec_destroy(h);
+  }
 
   void print_vector_info() {}  // src/gcre.h:144-152: all output is commented out upstream
 
@@ -115,7 +127,7 @@ class JoinExec {
     std::vector<double> flat(rows * cols, -1.0);  // ragged rows read as the reference's -1.0 padding
     for (size_t r = 0; r < rows; r++)
       for (size_t c = 0; c < std::min(cols, table[r].size()); c++) flat[r * cols + c] = table[r][c];
-    gcre_detail::raise(gcre_exec_set_value_table(handle_, flat.data(), (int)rows, (int)cols));
+    gcre_for_each_device(handles_.size(), [&](size_t d) { return gcre_exec_set_value_table(handles_[d], flat.data(), (int)rows, (int)cols); });
   }
 
   // src/join_base.cpp:85-125 (same WARN lines)
@@ -129,13 +141,14 @@ class JoinExec {
     }
     if ((size_t)iters_requested > data.size())
       printf("  ** WARN not enough permuted cases, some will be reused to match iterations - hope this is for testing!\n");
-    gcre_detail::raise(gcre_exec_set_permuted_cases_i32(handle_, flat.data(), (int)rows, (int)cols));
+    gcre_for_each_device(handles_.size(),
+                         [&](size_t d) { return gcre_exec_set_permuted_cases_i32(handles_[d], flat.data(), (int)rows, (int)cols); });
   }
 
   // src/join_base.cpp:156-161
   TPathSet createPathSet(st_pathset_size size) const {
-    gcre_pathset* ps = nullptr;
-    gcre_detail::raise(gcre_pathset_create(handle_, size, &ps));
+    std::vector<gcre_pathset*> ps(handles_.size(), nullptr);
+    gcre_for_each_device(handles_.size(), [&](size_t d) { return gcre_pathset_create(handles_[d], size, &ps[d]); });
     return TPathSet(new PathSet(ps, size, width_ul, (uint16_t)(width_ul * (int)method)));
   }
 
@@ -144,25 +157,92 @@ class JoinExec {
     static_assert(sizeof(uid_ref) == sizeof(gcre_uid_ref), "uid_ref layout must match the C ABI");
     printf("progress:");
     const int k = top_k > 0 ? top_k : 1;
-    std::vector<gcre_score> sc((size_t)k + 1);
-    int n_sc = 0;
+    const size_t nd = handles_.size();
+    const bool keep = paths_res.size != 0;
+    const gcre_uid_ref* u = reinterpret_cast<const gcre_uid_ref*>(uids.uids.data());
+    const uint32_t n_uids = (uint32_t)uids.uids.size();
+
+    // shards of upstream rows balanced by pair count (score-only joins on several GPUs); one shard otherwise
+    std::vector<uint32_t> cut(nd + 1, n_uids);
+    cut[0] = 0;
+    if (nd > 1 && !keep) {
+      st_path_count total = uids.count_total_paths(), run = 0;
+      size_t next = 1;
+      for (uint32_t i = 0; i < n_uids && next < nd; i++) {
+        run += uids.uids[i].count > 0 ? uids.uids[i].count : 0;
+        while (next < nd && run * nd >= total * next) cut[next++] = i + 1;
+      }
+    }
+
+    std::vector<std::vector<gcre_score>> sc(nd, std::vector<gcre_score>((size_t)k + 1));
+    std::vector<int> n_sc(nd, 0);
+    std::vector<std::vector<double>> perm(nd, std::vector<double>((size_t)std::max(iters_requested, 1), 0.0));
+    gcre_for_each_device(nd, [&](size_t d) {
+      gcre_join_opts opts;
+      std::memset(&opts, 0, sizeof opts);
+      if (nd > 1 && !keep) {
+        if (cut[d] == cut[d + 1]) return (int)GCRE_OK;  // empty shard
+        opts.uid_begin = cut[d];
+        opts.uid_end = cut[d + 1];
+      }
+      return gcre_join(handles_[d], uids.path_length, u, n_uids, uids.signs.data(), (uint32_t)uids.signs.size(), paths0.handle(d),
+                       paths1.handle(d), paths_res.handle(d), k, sc[d].data(), &n_sc[d], perm[d].data(), &opts);
+    });
+
     joined_res res;
     res.permuted_scores.assign((size_t)iters_requested, 0.0);
-    double dummy = 0.0;
-    gcre_detail::raise(gcre_join(handle_, uids.path_length, reinterpret_cast<const gcre_uid_ref*>(uids.uids.data()), (uint32_t)uids.uids.size(),
-                                 uids.signs.data(), (uint32_t)uids.signs.size(), paths0.handle(), paths1.handle(), paths_res.handle(), k, sc.data(),
-                                 &n_sc, iters_requested ? res.permuted_scores.data() : &dummy, nullptr));
-    res.scores.reserve((size_t)n_sc);
-    for (int i = 0; i < n_sc; i++) res.scores.push_back(Score(sc[i].score, sc[i].src, sc[i].trg, sc[i].cases, sc[i].ctrls));
+    std::vector<gcre_score> merged((size_t)k + 1);
+    int n_merged = 0;
+    if (nd > 1 && !keep) {
+      // merge_scores of the reference (src/methods.h:25-39): element-wise max of the maxima, union of the top-K lists
+      for (size_t d = 0; d < nd; d++)
+        for (int r = 0; r < iters_requested; r++) res.permuted_scores[r] = std::max(res.permuted_scores[r], perm[d][r]);
+      std::vector<gcre_score> all;
+      std::vector<int> sizes;
+      for (size_t d = 0; d < nd; d++) {
+        all.insert(all.end(), sc[d].begin(), sc[d].begin() + n_sc[d]);
+        sizes.push_back(n_sc[d]);
+      }
+      gcre_detail::raise(gcre_merge_topk(all.data(), sizes.data(), (int)nd, k, merged.data(), &n_merged));
+    } else {
+      for (int r = 0; r < iters_requested; r++) res.permuted_scores[r] = perm[0][r];
+      merged = sc[0];
+      n_merged = n_sc[0];
+    }
+    res.scores.reserve((size_t)n_merged);
+    for (int i = 0; i < n_merged; i++) res.scores.push_back(Score(merged[i].score, merged[i].src, merged[i].trg, merged[i].cases, merged[i].ctrls));
     printf(" - done!\n\n");
     return res;
   }
 
-  gcre_exec* handle() const { return handle_; }
+  gcre_exec* handle(size_t device_slot = 0) const { return handles_[device_slot]; }
+  size_t device_count() const { return handles_.size(); }
 
  protected:
   static int padded_iterations(int iters) { return ((std::max(iters, 1) + 127) / 128) * 128; }
-  gcre_exec* handle_ = nullptr;
+
+  static std::vector<int> devices_from_env() {
+    std::vector<int> out;
+    if (const char* list = std::getenv("GCRE_DEVICES")) {
+      const char* p = list;
+      while (*p) {
+        char* e = nullptr;
+        const long v = std::strtol(p, &e, 10);
+        if (e == p) break;
+        out.push_back((int)v);
+        p = (*e == ',') ? e + 1 : e;
+      }
+    } else if (const char* n = std::getenv("GCRE_GPUS")) {
+      for (int d = 0; d < std::atoi(n); d++) out.push_back(d);
+    }
+    if (out.empty()) {
+      const char* dev = std::getenv("GCRE_DEVICE");
+      out.push_back(dev ? std::atoi(dev) : 0);
+    }
+    return out;
+  }
+
+  std::vector<gcre_exec*> handles_;
 };
 
 #endif
