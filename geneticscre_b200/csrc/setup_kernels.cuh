@@ -156,4 +156,62 @@ __global__ void build_diag_kernel(const double* __restrict__ vt, int rows, int c
   }
 }
 
+// ---- join index (UidRelSet) preparation on the device ---------------------------------------------------------------
+// uid_ref array-of-structs (src/gcre_types.h:50-56; 24 bytes each) -> the arrays the join kernels read, plus the inputs
+// of the two prefix sums (pairs per row, work units per row) and the bounds the pre-checks need.
+struct UidRefPOD {
+  int32_t src, trg, count;
+  uint32_t location;
+  unsigned long long path_idx;
+};
+
+struct UidStats {
+  unsigned long long max_loc_end;   // max(location + count) over rows with count > 0
+  unsigned long long max_res_end;   // max(path_idx + count)
+  unsigned int res_not_prefix;      // != 0 if some path_idx differs from the running sum of counts
+};
+
+__global__ void split_uids_kernel(const UidRefPOD* __restrict__ uids, uint32_t n, int partners_per_unit, int32_t* __restrict__ count,
+                                  uint32_t* __restrict__ loc, unsigned long long* __restrict__ res, unsigned long long* __restrict__ pairs_in,
+                                  unsigned long long* __restrict__ units_in, UidStats* __restrict__ stats) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long le = 0, re = 0;
+  if (u < n) {
+    const UidRefPOD r = uids[u];
+    const int32_t c = r.count > 0 ? r.count : 0;
+    count[u] = c;
+    loc[u] = r.location;
+    res[u] = r.path_idx;
+    pairs_in[u] = (unsigned long long)c;
+    units_in[u] = ((unsigned long long)c + partners_per_unit - 1) / partners_per_unit;
+    if (c > 0) {
+      le = (unsigned long long)r.location + c;
+      re = r.path_idx + c;
+    }
+  } else if (u == n) {  // the scans run over n + 1 entries
+    pairs_in[u] = 0;
+    units_in[u] = 0;
+  }
+  // warp-level max, then one atomic per warp
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    le = max(le, __shfl_xor_sync(0xffffffffu, le, d));
+    re = max(re, __shfl_xor_sync(0xffffffffu, re, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (le) atomicMax(&stats->max_loc_end, le);
+    if (re) atomicMax(&stats->max_res_end, re);
+  }
+}
+
+// after the scans: unit -> upstream row table, and the "result rows are the running sums" check
+__global__ void finish_uids_kernel(uint32_t n, const int32_t* __restrict__ count, const unsigned long long* __restrict__ res,
+                                   const unsigned long long* __restrict__ prefix, const unsigned long long* __restrict__ units,
+                                   uint32_t* __restrict__ unit_idx, UidStats* __restrict__ stats) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  if (count[u] > 0 && res[u] != prefix[u]) stats->res_not_prefix = 1;
+  for (unsigned long long q = units[u]; q < units[u + 1]; q++) unit_idx[q] = u;
+}
+
 }  // namespace gcre

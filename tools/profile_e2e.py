@@ -8,6 +8,7 @@ class A: pass
 a = A(); a.__dict__.update(bench.WORKLOAD); a.table = "auto"
 w, _ = bench.make_workload(a)
 lv = w.net.levels; n = w.n_patients
+import os as _os; _os.environ.setdefault("GCRE_TRACE_OFF","1")
 def T(label, t0):
     torch.cuda.synchronize(); print(f"  {label:28s} {(time.perf_counter()-t0)*1e3:9.2f} ms"); return time.perf_counter()
 data1_i = torch.from_numpy(synth.unpack_bits(w.gene_bits, n)).pin_memory().numpy()
