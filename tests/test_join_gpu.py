@@ -251,3 +251,42 @@ def test_wide_carrier_indices(engine, oracles, method, monkeypatch):
     for lvl in want:
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
         assert got[lvl].info["kernel"] == _lib.KERNEL_SPARSE
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_empty_and_all_zero_count_joins(engine, oracles, kernel):
+    """No upstream rows at all, and upstream rows that all have count 0 with R's location -1: sentinel only, zero maxima."""
+    ex = engine.JoinExec("method2", 9, 8, 5)
+    ex.kernel = kernel
+    ex.top_k = 3
+    ex.setValueTable(synth.make_value_table(9, 8))
+    ex.setPermutedMasks(synth.make_perm_masks(9, 8, 5, seed=1))
+    U = engine.UidRelSet
+    p1 = ex.createPathSet(4)
+    for uids, p0 in ((U(4, [], [], [], [], []), ex.createPathSet(0)),
+                     (U(4, [1, 2], [3, 4], [0, 0], [0xFFFFFFFF, 0xFFFFFFFF], [1, -1]), ex.createPathSet(2))):
+        r = ex.join(uids, p0, p1, ex.createPathSet(0))
+        assert [(s.score, s.src, s.trg) for s in r.scores] == [(-math.inf, -1, -1)]
+        assert r.permuted_scores.tolist() == [0.0] * 5 and r.info["pairs"] == 0
+
+
+def test_resident_join_index_matches_one_shot(engine):
+    """UidRelSet.make_resident (join index kept on the device) gives the same results as passing the arrays per join,
+    also for a shard of the upstream rows."""
+    w = synth.make_workload(50, 60, 90, 300, 40, seed=77, max_path_length=4, real_table=True, max_freq=0.15, zero_frac=0.2)
+    ex = engine.JoinExec("method2", w.n_cases, w.n_ctrls, w.n_perms)
+    ex.top_k = 5
+    ex.setValueTable(w.value_table)
+    ex.setPermutedMasks(w.perm_masks)
+    from geneticscre_b200 import schedule
+
+    _, kept = schedule.replay_levels(ex, engine.UidRelSet, w, 3, only=())
+    lv = w.net.levels["4"]
+    zero = ex.createPathSet(0)
+    a = engine.UidRelSet(4, lv.src, lv.trg, lv.count, lv.location, lv.signs)
+    b = engine.UidRelSet(4, lv.src, lv.trg, lv.count, lv.location, lv.signs).make_resident(ex)
+    for rng in (None, (lv.n_uids // 4, lv.n_uids // 2)):
+        ra = ex.join(a, kept["paths3"], kept["paths2"], zero, uid_range=rng)
+        rb = ex.join(b, kept["paths3"], kept["paths2"], zero, uid_range=rng)
+        helpers.assert_same_results(rb, ra, what=f"resident vs one-shot {rng}")
+        assert ra.info["pairs"] == rb.info["pairs"] > 0
