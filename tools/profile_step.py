@@ -7,6 +7,7 @@ import bench
 class A: pass
 a = A(); a.__dict__.update(bench.WORKLOAD); a.table = "auto"
 if len(sys.argv) > 2: a.n_edges = int(sys.argv[2])
+if len(sys.argv) > 3: a.n_perms = int(sys.argv[3])
 w, _ = bench.make_workload(a)
 lv = w.net.levels
 kernel = {"dense": 1, "sparse": 2}[sys.argv[1] if len(sys.argv) > 1 else "sparse"]
