@@ -1,0 +1,112 @@
+"""Decorated p-values of the reported top-K paths (reference: R/DecoratedPvalue.R:49-304).
+
+For every top-K path of length L and every split point, the path is cut into a sub-path (the first j genes, or the last
+ones for the backward direction) and the next gene; the carriers that gene ADDS to the sub-path are re-drawn uniformly
+without replacement among the patients the sub-path does not cover, the path is re-scored from the value table, and the
+decorated p-value is the share of redraws scoring at least as high as the real path (computeDecoratedPvalue,
+R/DecoratedPvalue.R:198-304).
+
+This is host-side post-processing of <= K * L * 2(L-1) sub-paths - not part of the join loop and not worth a kernel.  Only
+the number of redrawn carriers that fall among the cases matters, and that number is hypergeometric, so besides the
+reference's Monte-Carlo estimate (`n_permutations` redraws; R's `sample()` stream cannot be reproduced, a seeded numpy
+generator is used) the exact limit of that estimate is available (`n_permutations=None`): the tail probability is summed
+over the support of the (independent) positive and negative hypergeometric counts.  Stratified resampling
+(R/DecoratedPvalue.R:229-262) is not implemented.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def _hypergeom_pmf(n_good: int, n_bad: int, n_draw: int) -> tuple[np.ndarray, np.ndarray]:
+    """Support and probabilities of the number of 'good' items among n_draw drawn without replacement."""
+    from scipy.special import gammaln
+
+    lo, hi = max(0, n_draw - n_bad), min(n_draw, n_good)
+    x = np.arange(lo, hi + 1)
+
+    def lch(a, b):
+        return gammaln(a + 1.0) - gammaln(b + 1.0) - gammaln(a - b + 1.0)
+
+    logp = lch(n_good, x) + lch(n_bad, n_draw - x) - lch(n_good + n_bad, n_draw)
+    p = np.exp(logp)
+    return x, p / p.sum()
+
+
+@dataclass
+class DecoratedResult:
+    decorated_pvalue: float
+    cases1: int
+    controls1: int
+    cases2: int
+    controls2: int
+    score: float
+
+
+def compute_decorated_pvalue(pos1, neg1, pos2, neg2, n_cases: int, n_ctrls: int, method: int, value_table: np.ndarray,
+                             n_permutations: int | None = None, rng: np.random.Generator | None = None) -> DecoratedResult:
+    """computeDecoratedPvalue (R/DecoratedPvalue.R:198-304) for boolean patient vectors (cases first).
+
+    pos1/neg1: carriers of the sub-path (positive / negative part); pos2/neg2: carriers of the gene being added.
+    """
+    pos1, neg1, pos2, neg2 = (np.asarray(v, dtype=bool) for v in (pos1, neg1, pos2, neg2))
+    n = n_cases + n_ctrls
+    is_case = np.arange(n) < n_cases
+    pos2 = pos2 & ~pos1  # only what the gene adds (R/DecoratedPvalue.R:206-209)
+    neg2 = neg2 & ~neg1
+    # counts as in R/DecoratedPvalue.R:218-225: the negative part counts controls as "cases"
+    case_pos1, case_neg1 = int((pos1 & is_case).sum()), int((neg1 & ~is_case).sum())
+    ctrl_pos1, ctrl_neg1 = int((pos1 & ~is_case).sum()), int((neg1 & is_case).sum())
+    case_pos2, case_neg2 = int((pos2 & is_case).sum()), int((neg2 & ~is_case).sum())
+    ctrl_pos2, ctrl_neg2 = int((pos2 & ~is_case).sum()), int((neg2 & is_case).sum())
+    vt = np.asarray(value_table)
+
+    def score_of(cp, tp, cn, tn):
+        """cp of tp redrawn positive carriers are cases; cn of tn redrawn negative carriers are controls."""
+        if method == 1:  # R/DecoratedPvalue.R:226-227, 285-286
+            return vt[case_pos1 + cp + case_neg1 + cn, ctrl_pos1 + (tp - cp) + ctrl_neg1 + (tn - cn)]
+        return vt[case_pos1 + cp, ctrl_pos1 + (tp - cp)] + vt[case_neg1 + cn, ctrl_neg1 + (tn - cn)]  # :228-229, :287-288
+
+    k_pos, k_neg = int(pos2.sum()), int(neg2.sum())
+    score = float(score_of(case_pos2, k_pos, case_neg2, k_neg))
+    # pools the carriers are redrawn from (R/DecoratedPvalue.R:232-233): everything outside the sub-path
+    good_pos, bad_pos = int((~pos1 & is_case).sum()), int((~pos1 & ~is_case).sum())    # "good" = a case
+    good_neg, bad_neg = int((~neg1 & ~is_case).sum()), int((~neg1 & is_case).sum())    # "good" = a control
+    if n_permutations is None:
+        xp, pp = _hypergeom_pmf(good_pos, bad_pos, k_pos)
+        xn, pn = _hypergeom_pmf(good_neg, bad_neg, k_neg)
+        s = score_of(xp[:, None], k_pos, xn[None, :], k_neg)
+        pvalue = float((pp[:, None] * pn[None, :])[s >= score].sum())
+    else:
+        rng = rng or np.random.default_rng(0)
+        cp = rng.hypergeometric(good_pos, bad_pos, k_pos, size=n_permutations) if k_pos else np.zeros(n_permutations, dtype=np.int64)
+        cn = rng.hypergeometric(good_neg, bad_neg, k_neg, size=n_permutations) if k_neg else np.zeros(n_permutations, dtype=np.int64)
+        pvalue = float((score_of(cp, k_pos, cn, k_neg) >= score).mean())  # R/DecoratedPvalue.R:293
+    return DecoratedResult(pvalue, case_pos1 + case_neg1, ctrl_pos1 + ctrl_neg1, case_pos2 + case_neg2, ctrl_pos2 + ctrl_neg2, score)
+
+
+def decorated_pvalues_for_path(gene_rows: np.ndarray, signs, n_cases: int, n_ctrls: int, method: int, value_table: np.ndarray,
+                               n_permutations: int | None = None, rng: np.random.Generator | None = None) -> list[dict]:
+    """All forward and backward splits of one path (R/DecoratedPvalue.R:123-180).
+
+    gene_rows: bool/0-1 array [L][n] of the path's genes in order; signs: +1/-1 per gene (method 2 moves the genes with a
+    negative sign to the negative part, R/DecoratedPvalue.R:129-132).
+    """
+    rows = np.asarray(gene_rows) != 0
+    L = rows.shape[0]
+    signs = np.asarray(signs)
+    pos = rows.copy()
+    neg = np.zeros_like(rows)
+    if method == 2:
+        neg[signs == -1] = rows[signs == -1]
+        pos[signs == -1] = False
+    out = []
+    for j in range(1, L):  # forward: genes 1..j, then gene j+1
+        r = compute_decorated_pvalue(pos[:j].any(0), neg[:j].any(0), pos[j], neg[j], n_cases, n_ctrls, method, value_table, n_permutations, rng)
+        out.append({"direction": "Forward", "subpath1": list(range(j)), "subpath2": j, **r.__dict__})
+    for j in range(L - 1, 0, -1):  # backward: genes L..j+1, then gene j
+        r = compute_decorated_pvalue(pos[j:].any(0), neg[j:].any(0), pos[j - 1], neg[j - 1], n_cases, n_ctrls, method, value_table, n_permutations, rng)
+        out.append({"direction": "Backward", "subpath1": list(range(L - 1, j - 1, -1)), "subpath2": j - 1, **r.__dict__})
+    return out
