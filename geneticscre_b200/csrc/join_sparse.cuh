@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
   const CT* car1 = static_cast<const CT*>(s.car1);
   __shared__ uint32_t s_base[WARPS][M][16][32];          // base counts per warp / half / packed register / lane
   __shared__ __align__(16) uint32_t s_queue[WARPS][QCAP];  // row offsets (carrier * Iw) of the partner's carriers that survive the filter
+  // method 2: the two halves go through ONE instance of the filter / accumulate / flush code (a rolled loop), their counts
+  // parked here for the look-up stage: unrolled per half the kernel was 62 KB of SASS and lost more issue slots to
+  // instruction fetch than to memory latency (profiles/r1_sparse_final_full.txt, no_instruction 4.1 vs long_scoreboard 4.0)
+  __shared__ uint32_t s_cnt[WARPS][M == 2 ? 2 : 1][M == 2 ? 16 : 1][32];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Wp = a.Wp, Iw = a.Iw;  // Iw: words per patient row of pt (a multiple of 32: every lane owns a valid word)
@@ -276,14 +280,17 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     // ---- base: the upstream row's own carriers ----
     uint32_t t0[M], nc0[M];
 #pragma unroll
+    for (int h = 0; h < M; h++) t0[h] = nc0[h] = 0;
+#pragma unroll 1
     for (int h = 0; h < M; h++) {
       uint32_t acc[16];
 #pragma unroll
       for (int i = 0; i < 16; i++) acc[i] = 0;
       const size_t item = (size_t)idx * M + h;
       const uint32_t o = s.off0[item], plen = s.off0[item + 1] - o;
-      t0[h] = s.len0[item];
-      nc0[h] = s.ncase0[item];
+      const uint32_t t0h = s.len0[item], nc0h = s.ncase0[item];
+      if (M == 1 || h == 0) { t0[0] = t0h; nc0[0] = nc0h; } else { t0[M - 1] = t0h; nc0[M - 1] = nc0h; }
+#pragma unroll 1
       for (uint32_t i = 0; i < plen; i += 8) add8(acc, car0 + o + i);
       if (inbatch > 0) {
         flush_planes(acc, pl, bits_for(inbatch));
@@ -300,19 +307,20 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       const uint32_t loc = loc0 + j;
       bool flip = true;
       if (M == 2) flip = need_flip(a.path_length, a.signs, idx, loc);
-      uint32_t c16[M][16];
+      uint32_t c16[16];          // counts of the half being accumulated
       uint32_t nd[M], ncn[M];
 #pragma unroll
+      for (int h = 0; h < M; h++) nd[h] = ncn[h] = 0;
+#pragma unroll 1
       for (int h = 0; h < M; h++) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) c16[h][i] = s_base[warp][h][i][lane];
+        for (int i = 0; i < 16; i++) c16[i] = s_base[warp][h][i][lane];
         // joined half h = upstream half h | partner half hh   (src/methods.h:137-145)
         const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
         const size_t item = (size_t)loc * M + hh;
         const uint32_t o = s.off1[item], len = s.len1[item];
         const uint64_t* p0h = p0row + h * Wp;
-        nd[h] = 0;
-        ncn[h] = 0;
+        uint32_t ndh = 0, ncnh = 0;
         uint32_t qn = 0;  // carriers waiting in the queue (warp-uniform)
         for (uint32_t i0 = 0; i0 < len; i0 += 32) {
           const uint32_t i = i0 + lane;
@@ -321,35 +329,44 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           const uint32_t w0 = valid ? __ldg(reinterpret_cast<const uint32_t*>(p0h) + (c >> 5)) : 0u;
           const bool keep = valid && !((w0 >> (c & 31)) & 1u);   // not already a carrier of the upstream row
           const unsigned km = __ballot_sync(0xffffffffu, keep);
-          ncn[h] += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
+          ncnh += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
           if (keep) queue[qn + __popc(km & lt_mask)] = c * (uint32_t)Iw;
           qn += __popc(km);
           if (qn >= 64) {  // drain eight groups, move the remainder (< 32 entries) to the front
             __syncwarp();
 #pragma unroll 1
             for (int gq = 0; gq < 8; gq++)
-              add8_off(c16[h], *reinterpret_cast<const uint4*>(queue + gq * 8), *reinterpret_cast<const uint4*>(queue + gq * 8 + 4));
+              add8_off(c16, *reinterpret_cast<const uint4*>(queue + gq * 8), *reinterpret_cast<const uint4*>(queue + gq * 8 + 4));
             const uint32_t rem = qn - 64;
             const uint32_t keepv = (lane < rem) ? queue[64 + lane] : 0u;
             __syncwarp();
             if (lane < rem) queue[lane] = keepv;
-            nd[h] += 64;
+            ndh += 64;
             qn = rem;
           }
         }
-        nd[h] += qn;
+        ndh += qn;
         if (qn > 0) {
           // pad to a multiple of 8 with the zero row and drain
           const uint32_t padded = (qn + 7u) & ~7u;
           if (lane < padded - qn) queue[qn + lane] = (uint32_t)s.n * (uint32_t)Iw;
           __syncwarp();
+#pragma unroll 1
           for (uint32_t gq = 0; gq < padded / 8; gq++)
-            add8_off(c16[h], *reinterpret_cast<const uint4*>(queue + gq * 8), *reinterpret_cast<const uint4*>(queue + gq * 8 + 4));
+            add8_off(c16, *reinterpret_cast<const uint4*>(queue + gq * 8), *reinterpret_cast<const uint4*>(queue + gq * 8 + 4));
           __syncwarp();
         }
         if (inbatch > 0) {
-          flush_planes(c16[h], pl, bits_for(inbatch));
+          flush_planes(c16, pl, bits_for(inbatch));
           inbatch = 0;
+        }
+        if (M == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) s_cnt[warp][h][i][lane] = c16[i];
+          if (h == 0) { nd[0] = ndh; ncn[0] = ncnh; } else { nd[M - 1] = ndh; ncn[M - 1] = ncnh; }
+        } else {
+          nd[0] = ndh;
+          ncn[0] = ncnh;
         }
       }
 
@@ -362,7 +379,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           const float* row = a.diagF + diag_base(total);
 #pragma unroll
           for (int b = 0; b < 32; b++) {
-            const uint32_t v = c16[0][GCRE_C16_REG(b)];
+            const uint32_t v = c16[GCRE_C16_REG(b)];
             const uint32_t c = GCRE_C16_HI(b) ? (v >> 16) : (v & 0xffffu);
             best[b] = fmaxf(best[b], __ldg(row + c));
           }
@@ -372,7 +389,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           const double* rown = a.diagDM + diag_base(tn) + tn;
 #pragma unroll
           for (int b = 0; b < 32; b++) {
-            const uint32_t vp = c16[0][GCRE_C16_REG(b)], vn = c16[M - 1][GCRE_C16_REG(b)];
+            const uint32_t vp = s_cnt[warp][0][M == 2 ? GCRE_C16_REG(b) : 0][lane], vn = s_cnt[warp][M == 2 ? 1 : 0][M == 2 ? GCRE_C16_REG(b) : 0][lane];
             const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
             const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
             // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
