@@ -245,21 +245,24 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     int inbatch = 0;
 
     // add eight carriers of a list (sentinel entries hit the zero row) to the bit planes
-    auto add8 = [&](uint32_t (&c16)[16], const CT* lst8) {
+    // `last`: nothing more will be added to these counters - flush what the planes hold.  The overflow flush (planes
+    // nearly full) and the final flush are the same code on purpose: flush_planes is ~170 instructions and was inlined
+    // five times before.
+    auto add8 = [&](uint32_t (&c16)[16], const CT* lst8, bool last) {
       uint32_t c[8], x[8];
       load8(lst8, c);
 #pragma unroll
       for (int q = 0; q < 8; q++) x[q] = __ldg(pt_lane + c[q] * (uint32_t)Iw);
       hs8(pl, x);
       inbatch += 8;
-      if (inbatch > FLUSH_AT) {
-        flush_planes(c16, pl, 8);
+      if (inbatch > FLUSH_AT || last) {
+        flush_planes(c16, pl, bits_for(inbatch));
         inbatch = 0;
       }
     };
 
     // the same for eight pre-multiplied row offsets (filtered partner carriers, multiplied once per lane in the filter)
-    auto add8_off = [&](uint32_t (&c16)[16], const uint4 lo, const uint4 hi) {
+    auto add8_off = [&](uint32_t (&c16)[16], const uint4 lo, const uint4 hi, bool last) {
       uint32_t x[8];
       x[0] = __ldg(pt_lane + lo.x);
       x[1] = __ldg(pt_lane + lo.y);
@@ -271,8 +274,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       x[7] = __ldg(pt_lane + hi.w);
       hs8(pl, x);
       inbatch += 8;
-      if (inbatch > FLUSH_AT) {
-        flush_planes(c16, pl, 8);
+      if (inbatch > FLUSH_AT || last) {
+        flush_planes(c16, pl, bits_for(inbatch));
         inbatch = 0;
       }
     };
@@ -291,11 +294,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       const uint32_t t0h = s.len0[item], nc0h = s.ncase0[item];
       if (M == 1 || h == 0) { t0[0] = t0h; nc0[0] = nc0h; } else { t0[M - 1] = t0h; nc0[M - 1] = nc0h; }
 #pragma unroll 1
-      for (uint32_t i = 0; i < plen; i += 8) add8(acc, car0 + o + i);
-      if (inbatch > 0) {
-        flush_planes(acc, pl, bits_for(inbatch));
-        inbatch = 0;
-      }
+      for (uint32_t i = 0; i < plen; i += 8) add8(acc, car0 + o + i, i + 8 >= plen);
 #pragma unroll
       for (int i = 0; i < 16; i++) s_base[warp][h][i][lane] = acc[i];
     }
@@ -322,6 +321,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
         const uint64_t* p0h = p0row + h * Wp;
         uint32_t ndh = 0, ncnh = 0;
         uint32_t qn = 0;  // carriers waiting in the queue (warp-uniform)
+#pragma unroll 1
         for (uint32_t i0 = 0; i0 < len; i0 += 32) {
           const uint32_t i = i0 + lane;
           const bool valid = i < len;
@@ -332,33 +332,25 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           ncnh += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
           if (keep) queue[qn + __popc(km & lt_mask)] = c * (uint32_t)Iw;
           qn += __popc(km);
-          if (qn >= 64) {  // drain eight groups, move the remainder (< 32 entries) to the front
+          const bool last_chunk = i0 + 32 >= len;
+          if (qn >= 64 || (last_chunk && (qn > 0 || inbatch > 0))) {
+            // drain: everything (padded to a multiple of 8 with the zero row) after the last chunk, else eight groups with
+            // the remainder (< 32 entries) moved to the front
+            // (after the last chunk at least one group runs, if only of zero rows, so that counts an earlier drain left in
+            // the planes are flushed)
+            const uint32_t take = last_chunk ? max((qn + 7u) & ~7u, 8u) : 64u;
+            if (last_chunk && lane < take - qn) queue[qn + lane] = (uint32_t)s.n * (uint32_t)Iw;
             __syncwarp();
 #pragma unroll 1
-            for (int gq = 0; gq < 8; gq++)
-              add8_off(c16, *reinterpret_cast<const uint4*>(queue + gq * 8), *reinterpret_cast<const uint4*>(queue + gq * 8 + 4));
-            const uint32_t rem = qn - 64;
+            for (uint32_t q0 = 0; q0 < take; q0 += 8)
+              add8_off(c16, *reinterpret_cast<const uint4*>(queue + q0), *reinterpret_cast<const uint4*>(queue + q0 + 4), last_chunk && q0 + 8 >= take);
+            const uint32_t rem = last_chunk ? 0u : qn - 64u;
             const uint32_t keepv = (lane < rem) ? queue[64 + lane] : 0u;
             __syncwarp();
             if (lane < rem) queue[lane] = keepv;
-            ndh += 64;
+            ndh += qn - rem;
             qn = rem;
           }
-        }
-        ndh += qn;
-        if (qn > 0) {
-          // pad to a multiple of 8 with the zero row and drain
-          const uint32_t padded = (qn + 7u) & ~7u;
-          if (lane < padded - qn) queue[qn + lane] = (uint32_t)s.n * (uint32_t)Iw;
-          __syncwarp();
-#pragma unroll 1
-          for (uint32_t gq = 0; gq < padded / 8; gq++)
-            add8_off(c16, *reinterpret_cast<const uint4*>(queue + gq * 8), *reinterpret_cast<const uint4*>(queue + gq * 8 + 4));
-          __syncwarp();
-        }
-        if (inbatch > 0) {
-          flush_planes(c16, pl, bits_for(inbatch));
-          inbatch = 0;
         }
         if (M == 2) {
 #pragma unroll

@@ -290,3 +290,39 @@ def test_resident_join_index_matches_one_shot(engine):
         rb = ex.join(b, kept["paths3"], kept["paths2"], zero, uid_range=rng)
         helpers.assert_same_results(rb, ra, what=f"resident vs one-shot {rng}")
         assert ra.info["pairs"] == rb.info["pairs"] > 0
+
+
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_sparse_queue_drain_corner_cases(engine, oracles, method):
+    """Hand-built rows that hit the carrier-queue edge cases of the sparse kernel: exactly 64 new carriers followed by list
+    entries that are all already in the upstream row (a mid-list drain, then nothing left to drain but counts still in the
+    bit planes), 65 new carriers, and a partner that adds nothing."""
+    n_cases, n_ctrls, perms = 230, 170, 300
+    n = n_cases + n_ctrls
+    def row(*ranges):
+        v = np.zeros(n, dtype=np.int32)
+        for a, b in ranges:
+            v[a:b] = 1
+        return v
+    up = np.stack([row((200, 300)), row((10, 20), (390, 400))])
+    partners = np.stack([row((0, 64), (200, 264)), row((0, 65), (200, 210)), row((200, 300)), row((150, 399))])
+    table = synth.make_test_table(n_cases, n_ctrls, seed=9)
+    masks = synth.make_perm_masks(n_cases, n_ctrls, perms, seed=10)
+    out = []
+    for cls, ucls, kern in ((oracles.OracleExec, oracles.UidRelSet, None), (engine.JoinExec, engine.UidRelSet, _lib.KERNEL_SPARSE),
+                            (engine.JoinExec, engine.UidRelSet, _lib.KERNEL_DENSE)):
+        ex = cls(method, n_cases, n_ctrls, perms)
+        if kern is not None:
+            ex.kernel = kern
+        ex.top_k = 20
+        ex.setValueTable(table)
+        ex.setPermutedMasks(masks)
+        p0, p1 = ex.createPathSet(2), ex.createPathSet(4)
+        p0.load(up)
+        p1.load(partners)
+        res = ex.createPathSet(8)
+        uids = ucls(2, [0, 1], [0, 1], [4, 4], [0, 0], [1, -1, 1, -1])
+        out.append((ex.join(uids, p0, p1, res), res.to_numpy()))
+    for got, rows in out[1:]:
+        helpers.assert_same_results(got, out[0][0])
+        assert np.array_equal(rows, out[0][1])
