@@ -11,7 +11,8 @@
 //   unit  = (upstream row idx, a block of <= PB of its partners, a block of 1,024 permutations)
 //   base  : the upstream row's own carriers are accumulated once per unit        -> base counts (u16, shared memory)
 //   pair  : only the partner's carriers NOT already in the upstream row (bit test against the dense upstream row) are
-//           accumulated on top of the base; partners that add no carrier reuse the base evaluation
+//           accumulated on top of the base (ballot-compacted into a shared-memory queue of row offsets, drained eight at a
+//           time); partners that add no carrier reuse the base evaluation
 //   score : counts -> anti-diagonal value-table look-ups (src/methods.h:96-103, 220-230) -> running per-permutation
 //           max kept in registers across all units of the warp, merged at the end with one atomicMax per permutation
 //   true scores / top-K candidates / kept rows exactly as in the dense kernel.
