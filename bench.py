@@ -437,16 +437,23 @@ def main():
         sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
         int_peak = 148 * 16 * sm_mhz * 1e6 / 2.0  # 16 POPC32/clk/SM nominal, 2 per 64-bit word-op
         ach = alg_bytes / (ker_ms * 1e-3) / 1e9
-        traffic = None
-        try:  # DRAM bytes of the same launches from the committed ncu capture (only valid for the default workload)
+        traffic, issue = None, None
+        try:  # DRAM bytes / executed instructions of the same launches from the committed ncu captures (default workload only)
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             c = tj["config"]
             if kname == "sparse" and world == 1 and (c["patients"], c["edges"], c["permutations"], c["path_length"]) == (n, a.n_edges, a.n_perms, a.path_length):
-                traffic = sum(v for k, v in tj.items() if k.startswith("join_sparse_kernel"))
-        except (OSError, KeyError, ValueError):
+                caps = [v for k, v in tj.items() if k.startswith("join_sparse_kernel")]
+                traffic = sum(v["dram_bytes"] for v in caps)
+                issue_peak = 148 * 4 * sm_mhz * 1e6  # warp instructions / s: one per SM sub-partition per clock
+                issue = {"warp_instructions_per_step": sum(v["warp_instructions"] for v in caps),
+                         "achieved_warp_inst_per_s": sum(v["warp_instructions"] for v in caps) / (ker_ms * 1e-3),
+                         "peak_warp_inst_per_s": issue_peak,
+                         "frac": sum(v["warp_instructions"] for v in caps) / (ker_ms * 1e-3) / issue_peak,
+                         "note": "instruction counts from the ncu captures, time measured live: the binding roof of the sparse kernel is instruction issue"}
+        except (OSError, KeyError, ValueError, TypeError):
             pass
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
-                "algorithmic_bytes": alg_bytes,
+                "algorithmic_bytes": alg_bytes, "issue_roofline": issue,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "kernel": f"join_{kname}_kernel, level-{last} joins of methods 1+2 (this rank's shard)", "kernel_ms_per_step": ker_ms,
                 "kernel_share_of_step": ker_ms / ms_step,
