@@ -26,10 +26,13 @@ inline void raise(int status) {
 }  // namespace gcre_detail
 
 // Run fn(device_slot) for every device slot; slots > 0 run on their own host threads (the C ABI is thread safe: one
-// exec per device, thread-local error strings, a locked block cache).  Returns the first non-OK status.
+// exec per device, thread-local error strings, a locked block cache).  Throws like gcre_detail::raise on the first failure.
 template <typename Fn>
 inline int gcre_for_each_device(size_t n_devices, const Fn& fn) {
-  if (n_devices <= 1) return fn(0);
+  if (n_devices <= 1) {
+    gcre_detail::raise(fn(0));  // throws the reference's exception types on failure
+    return GCRE_OK;
+  }
   std::vector<int> status(n_devices, GCRE_OK);
   std::vector<std::string> message(n_devices);
   std::vector<std::thread> pool;
