@@ -415,7 +415,7 @@ extern "C" int gcre_exec_generate_value_table(gcre_exec* ex) {
   ex->vt_rows = nc + 1;
   ex->vt_cols = nt + 1;
   ex->diag_cap = -1;
-  // log-factorials on the host (the same std::lgamma values the numpy restatement uses via math.lgamma)
+  // log-factorials on the host (synth.make_value_table fetches the same table through gcre_log_factorial_table)
   std::vector<double> lf((size_t)n + 1);
   gcre_log_factorial_table(n, lf.data());
   const int m_max = std::min(nc, nt) + 1;
