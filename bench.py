@@ -241,7 +241,7 @@ def run_reference_arm(a):
     last = vals[-1] if vals else {"cores": arm.cores, "kind": arm.kind, "sample": ""}
     ms = 1e3 * float(np.mean([v["seconds"] for v in vals])) if vals else None
     line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "impl": "reference", "config": workload_config(a, w),
             "cpu_baseline": {"value": value, "unit": "pair*perm/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": value, "unit": "pair*perm/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
