@@ -58,6 +58,8 @@ def parse_args():
                     help="value table: numpy on the host and uploaded (what R does), or generated on the device (needed for n >= 50k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=2, choices=[1, 2],
+                    help="e2e leg: 2 = submit the two methods from two host threads (uploads of one overlap joins of the other); 1 = sequential")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per method for the baseline sample")
     for k, v in WORKLOAD.items():
         ap.add_argument("--" + k.replace("_", "-"), type=type(v), default=v)
@@ -315,7 +317,19 @@ def main():
         state[method] = dict(ex=ex, d1=d1, d2=d2, uid=uid, perm_t=torch.zeros(ex.iterations, dtype=torch.float32, device="cuda"),
                              perm_all=torch.zeros(ex.iterations * world, dtype=torch.float32, device="cuda"))
 
-    def schedule_resident(st, results):
+    def merge_last_level(st, results):
+        """The last level's one data-path collective (per-permutation maxima over NVLink) for a perm-sharded job."""
+        if not shard_perms:
+            return
+        ex = st["ex"]
+        # result assembly: every rank drops its block of maxima into a zeroed N x I vector and ONE NCCL
+        # allreduce(max) over NVLink merges them (maxima are >= +0, so max against the zeros is concatenation)
+        with torch.cuda.stream(st.get("stream", stream)):  # the stream the exec launches on
+            st["perm_all"].zero_()
+            _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_all"].data_ptr() + 4 * ex.iterations * rank, ex.iterations))
+            dist.all_reduce(st["perm_all"], op=dist.ReduceOp.MAX)
+
+    def schedule_resident(st, results, collective=True):
         """Levels 1a,1b,2,3,(4,5) with device-resident inputs; the last level is sharded across ranks."""
         ex, d1, d2, uid = st["ex"], st["d1"], st["d2"], st["uid"]
         zero = ex.createPathSet(0)
@@ -335,11 +349,8 @@ def main():
             res_set = ex.createPathSet(lv[k].n_pairs) if (keep or (k in ("2", "3") and a.path_length > int(k))) else zero
             if k == last and shard_perms:
                 r = ex.join(uid[k], prev, operand, res_set)
-                # result assembly: every rank drops its block of maxima into a zeroed N x I vector and ONE NCCL
-                # allreduce(max) over NVLink merges them (maxima are >= +0, so max against the zeros is concatenation)
-                st["perm_all"].zero_()
-                _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_all"].data_ptr() + 4 * ex.iterations * rank, ex.iterations))
-                dist.all_reduce(st["perm_all"], op=dist.ReduceOp.MAX)
+                if collective:
+                    merge_last_level(st, results)
             elif k == last and world > 1:
                 r = ex.join(uid[k], prev, operand, zero, uid_range=my_shard, skip_host_perm=True)
                 _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations))
@@ -464,6 +475,18 @@ def main():
                         "algorithmic bytes), so int_frac_nominal > 1 is its algorithmic speed-up over the dense roof, not a utilisation - it is issue/ALU-bound "
                         "(71 % issue slots active, ALU pipe 75 %, profiles/r1_sparse_m1_level4_full.txt)"}
 
+    # ---- the metric per level as well as in aggregate (kernel time of each join, CUDA events inside gcre_join) ----
+    per_level = None
+    if last_out is not None:
+        per_level = {}
+        for method in ("method1", "method2"):
+            per_level[method] = {}
+            for k in names:
+                inf = last_out[method][0][k]
+                kms = float(inf["kernel_ms"])
+                per_level[method][k] = {"pairs": int(inf["pairs"]), "kernel_ms": kms, "kernel": {1: "dense", 2: "sparse"}.get(inf["kernel"], "none"),
+                                        "pair_perm_per_s": (inf["pairs"] * w.n_perms / (kms * 1e-3)) if kms > 0 else None}
+
     # ---- end-to-end through the reference-facing calls with HOST buffers (R-facing int matrices), N GPUs ----
     e2e = None
     if not a.no_e2e and w.value_table is None:
@@ -479,24 +502,82 @@ def main():
         h2d = (data1_i.nbytes + data2_i.nbytes + perm_i.nbytes + table.nbytes) * 2  # per method
         d2h_holder = [0]
 
-        def step_e2e():
-            d2h = 0
-            for method in ("method1", "method2"):
+        uid_host = {k: api.UidRelSet(lv[k].path_length, lv[k].src, lv[k].trg, lv[k].count, lv[k].location, lv[k].signs) for k in names}
+
+        def pinned(arr):  # the join indices are host inputs like the matrices: page-locked, so their copies run at PCIe rate
+            t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).pin_memory()
+            return t.numpy().view(arr.dtype).reshape(arr.shape)
+
+        for u in uid_host.values():
+            u._packed, u.signs = pinned(u._packed), pinned(u.signs)
+        h2d += 2 * sum(u._packed.nbytes + u.signs.nbytes for u in uid_host.values())
+        # The two methods are independent jobs (two GWASPA() calls upstream).  Run from two host threads on two streams the
+        # second method's uploads hide under the first method's joins; the collectives stay on the main thread, in order.
+        overlap = a.e2e_threads > 1 and (world == 1 or shard_perms)
+        e2e_streams = {m: (torch.cuda.Stream() if overlap else stream) for m in ("method1", "method2")}
+
+        def e2e_method(method, results, gate_in, gate_out):
+            t_in = time.perf_counter()
+            try:
+                torch.cuda.set_device(local_rank)
+                if gate_in is not None:
+                    gate_in.wait()
+                t_go = time.perf_counter()
                 ex = api.JoinExec(method, w.n_cases, w.n_ctrls, w.n_perms, device=local_rank)
-                ex.set_stream(stream.cuda_stream)
+                ex.set_stream(e2e_streams[method].cuda_stream)
                 ex.kernel = kernel
                 ex.top_k = a.top_k
                 ex.setValueTable(table)
                 ex.setPermutedCases(perm_i)
                 d1 = ex.createPathSet(data1_i.shape[0]); d1.load(data1_i)
                 d2 = ex.createPathSet(data2_i.shape[0]); d2.load(data2_i)
-                st = dict(ex=ex, d1=d1, d2=d2, uid=state[method]["uid"], perm_t=state[method]["perm_t"], perm_all=state[method]["perm_all"])
-                res = {}
-                schedule_resident(st, res)
+            finally:
+                if gate_out is not None:
+                    gate_out.set()
+            t_up = time.perf_counter()
+            st = dict(ex=ex, d1=d1, d2=d2, uid=uid_host, stream=e2e_streams[method], perm_t=state[method]["perm_t"], perm_all=state[method]["perm_all"])
+            res = {}
+            schedule_resident(st, res, collective=not overlap)
+            results[method] = (st, res)
+            if dbg:
+                sys.stderr.write(f"[bench] e2e {method}: waited {(t_go - t_in) * 1e3:.1f} ms, uploads {(t_up - t_go) * 1e3:.1f} ms, "
+                                 f"joins {(time.perf_counter() - t_up) * 1e3:.1f} ms\n")
+
+        def step_e2e():
+            import threading
+
+            d2h = 0
+            results = {}
+            if overlap:
+                gate = threading.Event()
+                errs = []
+
+                def guarded(*args):
+                    try:
+                        e2e_method(*args)
+                    except BaseException as e:  # re-raised on the main thread
+                        errs.append(e)
+
+                th = [threading.Thread(target=guarded, args=("method2", results, None, gate)),
+                      threading.Thread(target=guarded, args=("method1", results, gate, None))]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                if errs:
+                    raise errs[0]
+                for method in ("method1", "method2"):
+                    merge_last_level(*results[method])
+            else:
+                for method in ("method1", "method2"):
+                    e2e_method(method, results, None, None)
+            for method in ("method1", "method2"):
+                st, res = results.pop(method)
                 for k, r in res.items():
                     if not k.startswith("_"):
                         d2h += r.permuted_scores.nbytes // 2 + len(r.scores) * 24
-                del res, st, d1, d2
+                ex = st["ex"]
+                del res, st
                 ex.close()
             d2h_holder[0] = d2h
 
@@ -515,7 +596,11 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": pp_step / float(dt.item()), "unit": "pair*perm/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_holder[0]),
                "ms_per_step": float(dt.item()) * 1e3, "steps": e2e_steps,
-               "note": "host IntegerMatrix data + CaseORControl int matrix + f64 value table + join indices uploaded every step (pinned), per method"}
+               "host_threads": 2 if overlap else 1,
+               "note": "host IntegerMatrix data + CaseORControl int matrix + f64 value table + join indices uploaded every step (pinned), per method; "
+                       "the two methods are submitted from two host threads on two streams, so one method's uploads overlap the other's joins"
+                       if overlap else
+                       "host IntegerMatrix data + CaseORControl int matrix + f64 value table + join indices uploaded every step (pinned), per method"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline and w.value_table is not None:
@@ -533,7 +618,7 @@ def main():
         line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (shard_perms or world == 1) else "strong", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,
-                "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu,
+                "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu, "per_level": per_level,
                 "pair_perm_per_step": pp_step, "workload_gen_s": round(gen_s, 1)}
         print(json.dumps(line))
     if world > 1:

@@ -16,6 +16,7 @@
 #include <unordered_map>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -69,8 +70,11 @@ struct PhaseTrace {
     line += buf;
     t = now;
   }
-  void done(const char* what) {
-    if (on) fprintf(stderr, "[gcre trace] %s:%s\n", what, line.c_str());
+  void done(const char* what) {  // tagged with the calling thread and the wall clock, so interleaved execs can be told apart
+    if (!on) return;
+    const double at = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    fprintf(stderr, "[gcre trace] t=%.3f thr=%04zx %s:%s\n", std::fmod(at, 1e6), std::hash<std::thread::id>()(std::this_thread::get_id()) & 0xffff, what,
+            line.c_str());
   }
 };
 
@@ -159,6 +163,7 @@ static std::map<int, BlockCache> g_cache;  // per device
 
 static cudaError_t dev_alloc(const gcre_exec* ex, void** out, size_t bytes);
 static void dev_free(const gcre_exec* ex, void* p);
+static void reap_staged(gcre_exec* ex, bool all);
 
 struct DevBuf {  // grow-only device scratch owned by one exec
   const gcre_exec* owner = nullptr;
@@ -185,6 +190,16 @@ struct gcre_exec {
   int M = 1, n_cases = 0, n_ctrls = 0, n = 0, W64 = 0, Wp = 0, iters = 0, Ip = 0, Iw = 0, device = 0, sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_piece = nullptr;                                  // upload throttling (copy_pieces)
+  cudaEvent_t ev_half[2] = {nullptr, nullptr};                     // staging halves of upload_staged's streamed path
+  // host -> device uploads run on their own stream so that they never queue behind (or wait for) kernels
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_order = nullptr;
+  struct Staged {
+    void* p;
+    cudaEvent_t consumed;
+  };
+  std::vector<Staged> staged;  // staging blocks whose unpack kernel may still be pending
   // permutation masks
   uint64_t* d_masks = nullptr;  // canonical perm-major [iters][W64]
   uint64_t* d_pm = nullptr;     // word-major [Wp][Ip]
@@ -256,6 +271,28 @@ static void dev_free(const gcre_exec* ex, void* p) {
   g_cache[ex->device].free(p, ex->stream);
 }
 
+// a block whose first use is on `stream` (the cache orders it after the block's previous life on any other stream)
+static cudaError_t dev_alloc_on(const gcre_exec* ex, void** out, size_t bytes, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  return g_cache[ex->device].alloc(out, bytes, stream);
+}
+
+// Staging blocks of upload_staged go back to the cache once their unpack kernel has run (or, with `all`, now: the cache
+// records the hand-back on ex->stream, behind that kernel).
+static void reap_staged(gcre_exec* ex, bool all) {
+  size_t kept = 0;
+  for (auto& st : ex->staged) {
+    if (all || cudaEventQuery(st.consumed) == cudaSuccess) {
+      dev_free(ex, st.p);
+      cudaEventDestroy(st.consumed);
+    } else {
+      ex->staged[kept++] = st;
+    }
+  }
+  ex->staged.resize(kept);
+  cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
+}
+
 // Return every cached (currently unused) device block to the driver.
 extern "C" int gcre_release_cached_memory(void) {
   std::lock_guard<std::mutex> lock(g_cache_mu);
@@ -316,6 +353,11 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
     ex->stream = ex->own_stream;
     CK(cudaEventCreate(&ex->ev0));
     CK(cudaEventCreate(&ex->ev1));
+    CK(cudaEventCreateWithFlags(&ex->ev_piece, cudaEventDisableTiming));
+    for (auto& e : ex->ev_half) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ex->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ex->ev_copy, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ex->ev_order, cudaEventDisableTiming));
     for (DevBuf* b : {&ex->cand, &ex->scratch, &ex->scan_tmp}) b->owner = ex;
     CK(dev_alloc(ex, (void**)&ex->d_masks, std::max<size_t>((size_t)iters * ex->W64, 1) * 8));
     CK(dev_alloc(ex, (void**)&ex->d_pm, (size_t)ex->Wp * ex->Ip * 8));
@@ -326,8 +368,7 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
     CK(dev_alloc(ex, (void**)&ex->d_scalars, 16 * sizeof(unsigned)));
     CK(cudaMemsetAsync(ex->d_scalars, 0, 16 * sizeof(unsigned), ex->stream));
     CK(cudaMallocHost(&ex->h_scalars, 16 * sizeof(unsigned)));
-    CK(cudaStreamSynchronize(ex->stream));
-    return GCRE_OK;
+    return GCRE_OK;  // no host sync: everything later is ordered on ex->stream (gcre_exec_set_stream carries the order over)
   }();
   if (rc != GCRE_OK) {
     gcre_exec_destroy(ex);
@@ -341,6 +382,8 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   if (!ex) return GCRE_OK;
   cudaSetDevice(ex->device);
   if (ex->own_stream) cudaStreamSynchronize(ex->own_stream);
+  if (ex->copy_stream) cudaStreamSynchronize(ex->copy_stream);
+  reap_staged(ex, true);
   for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
                   (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars})
     dev_free(ex, p);
@@ -350,6 +393,11 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   ex->scratch.release();
   if (ex->ev0) cudaEventDestroy(ex->ev0);
   if (ex->ev1) cudaEventDestroy(ex->ev1);
+  if (ex->ev_piece) cudaEventDestroy(ex->ev_piece);
+  for (auto e : ex->ev_half) if (e) cudaEventDestroy(e);
+  if (ex->ev_copy) cudaEventDestroy(ex->ev_copy);
+  if (ex->ev_order) cudaEventDestroy(ex->ev_order);
+  if (ex->copy_stream) cudaStreamDestroy(ex->copy_stream);
   if (ex->own_stream) cudaStreamDestroy(ex->own_stream);
   delete ex;
   return GCRE_OK;
@@ -371,8 +419,86 @@ extern "C" int gcre_exec_get_info(const gcre_exec* ex, gcre_exec_info* out) {
 extern "C" int gcre_exec_set_stream(gcre_exec* ex, void* cuda_stream) {
   if (!ex) return fail(GCRE_ERR_ARG, "null argument");
   CKS(use_device(ex));
+  cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ex->own_stream;
+  if (next != ex->stream) {  // work already queued on the old stream stays ahead of work on the new one (no host sync)
+    CK(cudaEventRecord(ex->ev_order, ex->stream));
+    CK(cudaStreamWaitEvent(next, ex->ev_order, 0));
+  }
+  ex->stream = next;
+  return GCRE_OK;
+}
+
+// Host -> device upload of `n_units` records of `unit_bytes` each, unpacked on the device by
+// consume(d_piece, first_unit, units) (a kernel launch on ex->stream).
+//
+// Up to kWholeBytes the records land in one staging block, copied on the exec's copy stream in 16 MB transfers, and the
+// unpack kernel follows on ex->stream behind an event; the host waits for the copies only.  Nothing here waits for a kernel,
+// so an upload proceeds at PCIe rate while another exec of the process has the SMs full with a join (a join kernel's
+// persistent CTAs hold every register of an SM until the kernel ends; an unpack kernel between two copies would wait for
+// that).  Larger inputs stream through
+// the two halves of ex->scratch on ex->stream, copy k+1 overlapping kernel k.  Either way the caller's host buffer is free
+// on return.
+constexpr size_t kCopyBytes = (size_t)16 << 20;
+constexpr size_t kWholeBytes = (size_t)2 << 30;
+constexpr size_t kStreamedPiece = (size_t)256 << 20;
+
+// One host -> device copy as 16 MB transfers, each issued only when the previous one has finished.  Measured on this box
+// (tools/copy_contention.py): a stream with copies queued back to back keeps the copy engine to itself - a 1 MB copy on
+// another stream waited 23 ms, the whole 1.2 GB upload, whether that was queued as one transfer or as 8 MB pieces two deep,
+// and a high-priority stream changed nothing; with one piece in flight the other stream waits one piece (0.33 ms at 16 MB)
+// and the upload still runs at 52 of 55 GB/s.  That matters when a second exec of the process is joining meanwhile.
+static int copy_pieces(gcre_exec* ex, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+  for (size_t b0 = 0; b0 < bytes; b0 += kCopyBytes) {
+    if (b0) CK(cudaEventSynchronize(ex->ev_piece));
+    CK(cudaMemcpyAsync(static_cast<char*>(dst) + b0, static_cast<const char*>(src) + b0, std::min(kCopyBytes, bytes - b0), cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(ex->ev_piece, stream));
+  }
+  return GCRE_OK;
+}
+
+template <class Consume>
+static int upload_staged(gcre_exec* ex, const void* src, size_t unit_bytes, size_t n_units, Consume&& consume) {
+  if (n_units == 0 || unit_bytes == 0) return GCRE_OK;
+  const size_t total = unit_bytes * n_units;
+  const char* force_streamed = std::getenv("GCRE_TEST_STREAMED_UPLOAD");  // test hook: piece size in bytes for the > 2 GB path
+  if (total <= kWholeBytes && !(force_streamed && *force_streamed)) {
+    reap_staged(ex, false);
+    gcre_exec::Staged st{nullptr, nullptr};
+    CK(dev_alloc_on(ex, &st.p, total, ex->copy_stream));
+    int rc = [&]() -> int {
+      CKS(copy_pieces(ex, st.p, src, total, ex->copy_stream));
+      CK(cudaEventRecord(ex->ev_copy, ex->copy_stream));
+      CK(cudaStreamWaitEvent(ex->stream, ex->ev_copy, 0));
+      CKS(consume(static_cast<const void*>(st.p), (size_t)0, n_units));
+      CK(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming));
+      CK(cudaEventRecord(st.consumed, ex->stream));
+      return GCRE_OK;
+    }();
+    if (rc != GCRE_OK || !st.consumed) {
+      cudaStreamSynchronize(ex->copy_stream);
+      cudaStreamSynchronize(ex->stream);
+      dev_free(ex, st.p);
+      if (st.consumed) cudaEventDestroy(st.consumed);
+      return rc != GCRE_OK ? rc : fail(GCRE_ERR_CUDA, "event creation failed");
+    }
+    ex->staged.push_back(st);
+    CK(cudaEventSynchronize(ex->ev_copy));
+    return GCRE_OK;
+  }
+  const size_t piece = (force_streamed && *force_streamed) ? std::max<size_t>(1, std::strtoull(force_streamed, nullptr, 10)) : kStreamedPiece;
+  const size_t per = std::max<size_t>(1, piece / unit_bytes);
+  const size_t half = (per * unit_bytes + 255) & ~(size_t)255;
+  CKS(ex->scratch.ensure(2 * half));
+  size_t k = 0;
+  for (size_t u0 = 0; u0 < n_units; u0 += per, k++) {
+    const size_t nu = std::min(per, n_units - u0);
+    char* d_piece = static_cast<char*>(ex->scratch.p) + (k & 1) * half;
+    if (k >= 2) CK(cudaEventSynchronize(ex->ev_half[k & 1]));  // the kernel that read this half two pieces ago is done
+    CKS(copy_pieces(ex, d_piece, static_cast<const char*>(src) + u0 * unit_bytes, nu * unit_bytes, ex->stream));
+    CKS(consume(static_cast<const void*>(d_piece), u0, nu));
+    CK(cudaEventRecord(ex->ev_half[k & 1], ex->stream));
+  }
   CK(cudaStreamSynchronize(ex->stream));
-  ex->stream = cuda_stream ? (cudaStream_t)cuda_stream : ex->own_stream;
   return GCRE_OK;
 }
 
@@ -380,16 +506,17 @@ extern "C" int gcre_exec_set_value_table(gcre_exec* ex, const double* table, int
   if (!ex || (!table && rows > 0 && cols > 0)) return fail(GCRE_ERR_ARG, "null argument");
   if (rows < 0 || cols < 0) return fail(GCRE_ERR_ARG, "negative table size");
   CKS(use_device(ex));
-  CK(cudaStreamSynchronize(ex->stream));
-  dev_free(ex, ex->d_vt);
+  dev_free(ex, ex->d_vt);  // stream-ordered: the cache guards the block with an event on ex->stream
   ex->d_vt = nullptr;
   // the reference keeps at most the top-left (n+1)x(n+1) block (src/join_base.cpp:74-78); larger inputs are legal
   ex->vt_rows = rows;
   ex->vt_cols = cols;
   const size_t bytes = std::max<size_t>((size_t)rows * cols, 1) * 8;
-  CK(dev_alloc(ex, (void**)&ex->d_vt, bytes));
-  if ((size_t)rows * cols > 0) CK(cudaMemcpyAsync(ex->d_vt, table, (size_t)rows * cols * 8, cudaMemcpyHostToDevice, ex->stream));
-  CK(cudaStreamSynchronize(ex->stream));
+  CK(dev_alloc_on(ex, (void**)&ex->d_vt, bytes, ex->copy_stream));
+  CKS(copy_pieces(ex, ex->d_vt, table, (size_t)rows * cols * 8, ex->copy_stream));
+  CK(cudaEventRecord(ex->ev_copy, ex->copy_stream));
+  CK(cudaStreamWaitEvent(ex->stream, ex->ev_copy, 0));
+  CK(cudaEventSynchronize(ex->ev_copy));  // the caller's table is free again; readers on ex->stream are ordered behind the copy
   ex->diag_cap = -1;  // anti-diagonal tables are rebuilt on the next join
   return GCRE_OK;
 }
@@ -490,27 +617,21 @@ extern "C" int gcre_exec_set_permuted_cases_i32(gcre_exec* ex, const int32_t* pe
   // src/join_base.cpp:116-123 would divide by zero with no rows and iters > 0: reject instead
   if (ex->iters > 0 && rows == 0) return fail(GCRE_ERR_ASSERT, "assertion");
   CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)ex->iters * ex->W64, 1) * 8, ex->stream));
-  // upload and pack in row blocks of <= 256 MB
-  const int rows_per_blk = (int)std::max<size_t>(1, ((size_t)256 << 20) / ((size_t)std::max(cols, 1) * 4));
-  CKS(ex->scratch.ensure((size_t)std::min(rows_per_blk, std::max(have, 1)) * std::max(cols, 1) * 4));
-  for (int r0 = 0; r0 < have; r0 += rows_per_blk) {
-    const int nr = std::min(rows_per_blk, have - r0);
-    CK(cudaMemcpyAsync(ex->scratch.p, perm + (size_t)r0 * cols, (size_t)nr * cols * 4, cudaMemcpyHostToDevice, ex->stream));
+  CKS(upload_staged(ex, perm, (size_t)cols * 4, (size_t)std::max(have, 0), [&](const void* d_piece, size_t r0, size_t nr) {
     const long long warps = (long long)nr * ex->W64;
-    pack_perm_i32_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>((const int32_t*)ex->scratch.p, nr, cols, ex->n_cases, ex->W64,
-                                                                           ex->d_masks, r0);
+    pack_perm_i32_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>((const int32_t*)d_piece, (int)nr, cols, ex->n_cases, ex->W64, ex->d_masks,
+                                                                           (int)r0);
     CK(cudaGetLastError());
-      LAUNCHED();
-    CK(cudaStreamSynchronize(ex->stream));  // scratch is reused by the next block
-  }
+    LAUNCHED();
+    return (int)GCRE_OK;
+  }));
   if (have < ex->iters) {
     cycle_perm_rows_kernel<<<grid_for((long long)(ex->iters - have) * ex->W64, 256), 256, 0, ex->stream>>>(ex->d_masks, have, ex->iters, ex->W64);
     CK(cudaGetLastError());
       LAUNCHED();
   }
   CKS(rebuild_mask_layouts(ex));
-  CK(cudaStreamSynchronize(ex->stream));
-  return GCRE_OK;
+  return GCRE_OK;  // `perm` has been read (upload_staged waits for its copies); the kernels stay queued on ex->stream
 }
 
 extern "C" int gcre_exec_set_permuted_masks_u64(gcre_exec* ex, const uint64_t* masks, int n_perms) {
@@ -519,7 +640,7 @@ extern "C" int gcre_exec_set_permuted_masks_u64(gcre_exec* ex, const uint64_t* m
   if (ex->iters > 0 && n_perms <= 0) return fail(GCRE_ERR_ASSERT, "assertion");
   const int have = std::min(n_perms, ex->iters);
   CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)ex->iters * ex->W64, 1) * 8, ex->stream));
-  if (have > 0) CK(cudaMemcpyAsync(ex->d_masks, masks, (size_t)have * ex->W64 * 8, cudaMemcpyHostToDevice, ex->stream));
+  if (have > 0) CKS(copy_pieces(ex, ex->d_masks, masks, (size_t)have * ex->W64 * 8, ex->stream));
   if (have < ex->iters) {
     cycle_perm_rows_kernel<<<grid_for((long long)(ex->iters - have) * ex->W64, 256), 256, 0, ex->stream>>>(ex->d_masks, have, ex->iters, ex->W64);
     CK(cudaGetLastError());
@@ -604,18 +725,14 @@ extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint
   if (rows == 0) return GCRE_OK;
   ps->zero_pending = false;
   CK(cudaMemsetAsync(ps->d_rows, 0, (size_t)ps->size * row_words(ex) * 8, ex->stream));
-  const uint32_t rows_per_blk = (uint32_t)std::max<size_t>(1, ((size_t)256 << 20) / ((size_t)std::max(cols, 1) * 4));
-  CKS(ex->scratch.ensure((size_t)std::min(rows_per_blk, rows) * std::max(cols, 1) * 4));
-  for (uint32_t r0 = 0; r0 < rows; r0 += rows_per_blk) {
-    const uint32_t nr = std::min(rows_per_blk, rows - r0);
-    CK(cudaMemcpyAsync(ex->scratch.p, data + (size_t)r0 * cols, (size_t)nr * cols * 4, cudaMemcpyHostToDevice, ex->stream));
+  CKS(upload_staged(ex, data, (size_t)cols * 4, rows, [&](const void* d_piece, size_t r0, size_t nr) {
     const long long warps = (long long)nr * ex->W64;
-    pack_rows_i32_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>((const int32_t*)ex->scratch.p, nr, cols,
-                                                                           ps->d_rows + (size_t)r0 * row_words(ex), (int)row_words(ex), ex->W64);
+    pack_rows_i32_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>((const int32_t*)d_piece, (uint32_t)nr, cols,
+                                                                           ps->d_rows + r0 * row_words(ex), (int)row_words(ex), ex->W64);
     CK(cudaGetLastError());
-      LAUNCHED();
-    CK(cudaStreamSynchronize(ex->stream));
-  }
+    LAUNCHED();
+    return (int)GCRE_OK;
+  }));
   ps->max_half_pop = -1;
   drop_view(ps);
   return GCRE_OK;
@@ -1051,6 +1168,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   CKS(uidset_bounds(us, ub, &pair_lo, &unit_lo));
   CKS(uidset_bounds(us, ue, &pair_hi, &unit_hi));
 
+  reap_staged(ex, true);  // upload staging blocks go back to the cache, stream-ordered behind their unpack kernels
   CKS(materialize_zero(const_cast<gcre_pathset*>(paths0)));
   CKS(materialize_zero(const_cast<gcre_pathset*>(paths1)));
   if (keep) {

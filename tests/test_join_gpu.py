@@ -81,6 +81,47 @@ def test_int_matrix_inputs(engine, oracles, method):
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
 
 
+def test_int_matrix_inputs_streamed_upload(engine, oracles, monkeypatch):
+    """Inputs above 2 GB stream through two staging halves; GCRE_TEST_STREAMED_UPLOAD forces that path with small pieces
+    (here 2,000 bytes: two to three rows per piece, many pieces, both halves reused)."""
+    monkeypatch.setenv("GCRE_TEST_STREAMED_UPLOAD", "2000")
+    w = synth.make_workload(90, 110, 100, 300, 50, seed=78, max_path_length=3, real_table=True, max_freq=0.1, zero_frac=0.2)
+    want, kw, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, "method2", 3, 6, use_int_matrices=True, int_perms=True)
+    got, kg, _ = helpers.run_schedule(engine.JoinExec, engine.UidRelSet, w, "method2", 3, 6, use_int_matrices=True, int_perms=True)
+    for k in kw:
+        assert np.array_equal(kg[k], kw[k])
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"streamed upload L{lvl}")
+
+
+def test_two_execs_on_two_host_threads(engine, oracles):
+    """Two execs driven from two host threads on their own streams (bench.py's e2e leg): uploads of one run beside the
+    joins of the other through the shared block cache; both must match the oracle."""
+    import threading
+
+    w = synth.make_workload(300, 340, 200, 900, 200, seed=79, max_path_length=4, real_table=True, max_freq=0.08, zero_frac=0.2)
+    want = {m: helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, m, 4, 8, use_int_matrices=True, int_perms=True)[0]
+            for m in ("method1", "method2")}
+    got, errs = {}, []
+
+    def work(method):
+        try:
+            for _ in range(3):
+                got[method] = helpers.run_schedule(engine.JoinExec, engine.UidRelSet, w, method, 4, 8, use_int_matrices=True, int_perms=True)[0]
+        except BaseException as e:
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(m,)) for m in ("method1", "method2")]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for m in want:
+        for lvl in want[m]:
+            helpers.assert_same_results(got[m][lvl], want[m][lvl], what=f"{m} L{lvl} (threaded)")
+
+
 @pytest.mark.parametrize("rows", [3, 20])
 def test_perm_rows_reused_or_truncated(engine, oracles, rows):
     """Fewer perm rows than iterations are reused cyclically, surplus rows ignored (src/join_base.cpp:89-90,116-123)."""
