@@ -235,7 +235,8 @@ class JoinExec:
                                       _ptr(uids.signs, C.c_int32), uids.signs.shape[0], paths0._h, paths1._h, res_h, int(self.top_k), sc,
                                       C.byref(n_sc), _ptr(perm, C.c_double), C.byref(opts)))
         scores = [Score(s.score, s.src, s.trg, s.cases, s.ctrls) for s in sc[: n_sc.value]]
-        info = {"pairs": int(opts.pairs_scored), "kernel_ms": float(opts.kernel_ms), "kernel": int(opts.kernel_used), "launches": int(opts.launches)}
+        info = {"pairs": int(opts.pairs_scored), "kernel_ms": float(opts.kernel_ms), "kernel": int(opts.kernel_used), "launches": int(opts.launches),
+                "precounted": bool(opts.precounted)}
         return joined_res(scores, perm[: self.iters_requested].copy(), info)
 
     def device_perm_max(self):

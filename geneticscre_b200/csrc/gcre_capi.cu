@@ -205,6 +205,7 @@ struct gcre_exec {
   uint64_t* d_pm = nullptr;     // word-major [Wp][Ip]
   uint32_t* d_pt = nullptr;     // patient-major [n][Iw], built on first use by a sparse kernel
   bool pt_valid = false;
+  unsigned long long mask_gen = 1;  // bumped whenever the permutation masks change: per-path-set pre-count tables depend on them
   // value table
   double* d_vt = nullptr;
   int vt_rows = 0, vt_cols = 0;
@@ -252,6 +253,7 @@ static void drop_view(gcre_pathset* ps) {
   dev_free(ps->ex, ps->view.len);
   dev_free(ps->ex, ps->view.ncase);
   dev_free(ps->ex, ps->view.car);
+  dev_free(ps->ex, ps->view.pcnt);
   ps->view = SparseView();
 }
 
@@ -591,6 +593,7 @@ static int rebuild_mask_layouts(gcre_exec* ex) {
       LAUNCHED();
   }
   ex->pt_valid = false;
+  ex->mask_gen++;
   return GCRE_OK;
 }
 
@@ -928,7 +931,14 @@ extern "C" int gcre_merge_topk(const gcre_score* lists, const int* list_sizes, i
 static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
   if (ps->view.valid) return GCRE_OK;
   CKS(materialize_zero(ps));
-  drop_view(ps);
+  {  // (re)build lists and stats; counts emitted with the rows stay - the rows have not changed
+    uint32_t* pcnt = ps->view.pcnt;
+    const unsigned long long gen = ps->view.pcnt_gen;
+    ps->view.pcnt = nullptr;
+    drop_view(ps);
+    ps->view.pcnt = pcnt;
+    ps->view.pcnt_gen = gen;
+  }
   const long long items = (long long)ps->size * ex->M;
   CK(dev_alloc(ex, (void**)&ps->view.off, (size_t)(items + 1) * 4));
   CK(dev_alloc(ex, (void**)&ps->view.len, std::max<size_t>(items, 1) * 4));
@@ -964,7 +974,28 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
     CK(cudaGetLastError());
     LAUNCHED();
   }
-  ps->view.valid = true;
+  ps->view.valid = ps->view.stats_valid = true;
+  return GCRE_OK;
+}
+
+// per-permutation counts of every (row, half) of a path set under the exec's current masks (join_sparse.cuh, PC kernels)
+static int ensure_precount(gcre_exec* ex, gcre_pathset* ps) {
+  if (ps->view.pcnt && ps->view.pcnt_gen == ex->mask_gen) return GCRE_OK;
+  dev_free(ex, ps->view.pcnt);
+  ps->view.pcnt = nullptr;
+  const long long items = (long long)ps->size * ex->M;
+  const int nb = ex->Iw / 32;
+  CK(dev_alloc(ex, (void**)&ps->view.pcnt, std::max<size_t>((size_t)items * nb, 1) * 2048));
+  if (items > 0) {
+    const unsigned grid = grid_for(items * nb * 32, 128);
+    if (sparse_wide(ex->n))
+      build_precount_kernel<uint32_t><<<grid, 128, 0, ex->stream>>>(ps->view.off, (const uint32_t*)ps->view.car, items, nb, ex->d_pt, ex->Iw, ps->view.pcnt);
+    else
+      build_precount_kernel<uint16_t><<<grid, 128, 0, ex->stream>>>(ps->view.off, (const uint16_t*)ps->view.car, items, nb, ex->d_pt, ex->Iw, ps->view.pcnt);
+    CK(cudaGetLastError());
+    LAUNCHED();
+  }
+  ps->view.pcnt_gen = ex->mask_gen;
   return GCRE_OK;
 }
 
@@ -1197,15 +1228,38 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   memset(&sp, 0, sizeof sp);
   if (kernel == GCRE_KERNEL_SPARSE) {
     CKS(ensure_patient_major(ex));
-    CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths0)));
+    // upstream operand: rows that came out of a KEEP join carry their counts and totals - no carrier lists needed
+    const bool base_emitted = paths0->view.pcnt && paths0->view.pcnt_gen == ex->mask_gen && paths0->view.stats_valid && paths0 != paths_res;
+    if (!base_emitted) CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths0)));
     CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths1)));
     sp.off0 = paths0->view.off; sp.len0 = paths0->view.len; sp.car0 = paths0->view.car; sp.ncase0 = paths0->view.ncase;
+    sp.pcnt0 = base_emitted ? paths0->view.pcnt : nullptr;
     sp.off1 = paths1->view.off; sp.len1 = paths1->view.len; sp.car1 = paths1->view.car; sp.ncase1 = paths1->view.ncase;
     sp.n = ex->n;
     sp.unit_prefix = (const unsigned long long*)us->units.p;
     sp.unit_idx = (const uint32_t*)us->unit_idx.p;
     sp.work_counter = (unsigned long long*)(ex->d_scalars + 2);
     sp.n_perm_blocks = ex->Iw / 32;
+    size_t budget = (size_t)24 << 30;  // device bytes a table of per-permutation counts may take (GCRE_PRECOUNT_MAX_MB overrides)
+    if (const char* mb = std::getenv("GCRE_PRECOUNT_MAX_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
+    // kept rows take their counts along (join_sparse.cuh) when the join writes all of them; GCRE_TEST_EMIT=0 (test hook) turns it off
+    const char* emit_env = std::getenv("GCRE_TEST_EMIT");
+    const bool emit = keep && pair_lo == 0 && pair_hi == total && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
+                      (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
+    if (!emit && precount_preferred(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget)) {
+      CKS(ensure_precount(ex, const_cast<gcre_pathset*>(paths1)));
+      sp.pcnt1 = paths1->view.pcnt;
+    }
+    if (keep && paths_res != paths0 && paths_res != paths1) drop_view(paths_res);  // its rows are about to be rewritten
+    if (emit) {
+      const size_t items = (size_t)paths_res->size * ex->M;
+      CK(dev_alloc(ex, (void**)&paths_res->view.pcnt, items * sp.n_perm_blocks * 2048));
+      CK(dev_alloc(ex, (void**)&paths_res->view.len, items * 4));
+      CK(dev_alloc(ex, (void**)&paths_res->view.ncase, items * 4));
+      sp.pcnt_res = paths_res->view.pcnt;
+      sp.len_res = paths_res->view.len;
+      sp.ncase_res = paths_res->view.ncase;
+    }
   }
 
   tr.mark("views");
@@ -1338,7 +1392,12 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   tr.mark("launches");
   if (keep) {
     paths_res->max_half_pop = (pair_lo == 0 && pair_hi == total) ? (long long)ex->h_scalars[1] : -1;
-    drop_view(paths_res);
+    if (sp.pcnt_res) {  // emitted with the rows
+      paths_res->view.pcnt_gen = ex->mask_gen;
+      paths_res->view.stats_valid = true;
+    } else {
+      drop_view(paths_res);
+    }
   }
 
   CKS(emit_topk(held, top_k, out_scores, n_scores));
@@ -1350,6 +1409,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     opts->kernel_ms = kernel_ms;
     opts->kernel_used = kernel;
     opts->launches = launches;
+    opts->precounted = sp.pcnt1 != nullptr;
   }
   return GCRE_OK;
 }

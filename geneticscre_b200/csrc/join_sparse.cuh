@@ -16,6 +16,19 @@
 //   score : counts -> anti-diagonal value-table look-ups (src/methods.h:96-103, 220-230) -> running per-permutation
 //           max kept in registers across all units of the warp, merged at the end with one atomicMax per permutation
 //   true scores / top-K candidates / kept rows exactly as in the dense kernel.
+//
+// Kept rows carry their counts forward.  A KEEP join has the per-permutation counts of every row it writes in registers
+// anyway; it stores them (2 KB per row, half and 1,024-permutation block, in the register image of this kernel) together
+// with the rows' carrier totals.  The next level, whose upstream operand those rows are, loads its base counts from that
+// table instead of walking the upstream carrier list per unit (a quarter of the level-4 gathers of BASELINE config 3) and
+// needs no carrier lists of the upstream set at all.
+//
+// Pre-counted partners (template flag PC).  When every partner row is joined with several upstream rows, its own
+// per-permutation counts P[row][half][perm] are formed once (build_precount_kernel) and a pair needs only
+//        count(up | partner) = count(up) + count(partner) - count(up & partner)
+// where up & partner - the partner's carriers that ARE already in the upstream row - is a handful of patients for
+// rare-variant rows (|up|*|partner|/n) instead of the ~|partner| carriers the delta formulation walks.  A pair then costs
+// one 2 KB read of P (coalesced, 4 x LDG.128 per lane), the filter pass over the partner's list and the look-ups.
 #pragma once
 #include <cstdlib>
 
@@ -35,7 +48,10 @@ constexpr int QCAP = 96;        // per-warp queue of filtered partner carriers (
 // (12 M pairs, ms per launch): method 1: 4 CTAs (128 regs) 19.9, 5: 17.4, 6: 16.2, 8 (64 regs, 164 B spilled) 15.0;
 // method 2: 4: 33.9, 5: 39.1, 6: 40.2, 8: 40.0.  Keeping the per-permutation state in shared memory instead (no
 // spills at 48 regs, 1,000 SASS instructions) was slower for both (22 / 35 ms): the kernel is issue-bound.
-constexpr int min_blocks(int m) { return m == 1 ? 8 : 4; }
+#ifndef GCRE_SPARSE_MB2
+#define GCRE_SPARSE_MB2 4
+#endif
+constexpr int min_blocks(int m) { return m == 1 ? 8 : GCRE_SPARSE_MB2; }
 }  // namespace sparse
 
 // Carrier-list (CSR) view of a path set: per (row, half) the ascending patient indices of its set bits.
@@ -48,7 +64,12 @@ struct SparseView {
   void* car = nullptr;        // [off[size*M]] patient indices: u16 when n <= 65,535, else u32
   uint32_t* ncase = nullptr;  // [size*M] carriers < n_cases (a prefix of the ascending list)
   size_t total = 0;           // padded entries
-  bool valid = false;
+  bool valid = false;         // lists (off, car) and stats (len, ncase) are built
+  bool stats_valid = false;   // len / ncase alone are filled (by the join that produced the rows): enough for an upstream operand with pcnt
+  // per-permutation counts of every (row, half), in the register image of the join kernel:
+  // [item][perm block][q = 0..3][lane][4] u32 = packed u16 pairs (registers 4q..4q+3 of GCRE_C16_REG) - 2 KB per block
+  uint32_t* pcnt = nullptr;
+  unsigned long long pcnt_gen = 0;  // exec->mask_gen the table was built for
 };
 
 struct SparseParams {
@@ -60,6 +81,11 @@ struct SparseParams {
   unsigned long long unit_begin, n_units;  // units of this launch
   unsigned long long* work_counter;
   int n_perm_blocks;                      // ceil(Iw / 32)
+  const uint32_t* pcnt1;                  // pre-counted partners (PC kernels), else null
+  const uint32_t* pcnt0;                  // per-permutation counts of the upstream rows (emitted by the join that made them), else null
+  uint32_t* pcnt_res;                     // KEEP: where to emit the counts / carrier totals of the kept rows, else null
+  uint32_t* len_res;
+  uint32_t* ncase_res;
 };
 
 // ---- view construction ----------------------------------------------------------------------------------------------
@@ -184,8 +210,45 @@ __device__ __forceinline__ void load8(const uint32_t* p, uint32_t (&c)[8]) {
   c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
 }
 
+// Pre-count table of a path set (see the header): one warp per (item, permutation block).
+template <typename CT>
+__global__ void __launch_bounds__(128) build_precount_kernel(const uint32_t* __restrict__ off, const CT* __restrict__ car, long long n_items, int n_perm_blocks,
+                                                             const uint32_t* __restrict__ pt, int Iw, uint32_t* __restrict__ pcnt) {
+  const int lane = threadIdx.x & 31;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_items * n_perm_blocks) return;
+  const long long item = w / n_perm_blocks;
+  const int pb = (int)(w % n_perm_blocks);
+  const uint32_t* pt_lane = pt + pb * 32 + lane;
+  const uint32_t o = off[item], plen = off[item + 1] - o;
+  uint32_t pl[8], c16[16];
+#pragma unroll
+  for (int j = 0; j < 8; j++) pl[j] = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) c16[i] = 0;
+  int inbatch = 0;
+#pragma unroll 1
+  for (uint32_t i = 0; i < plen; i += 8) {
+    uint32_t c[8], x[8];
+    load8(car + o + i, c);
+#pragma unroll
+    for (int q = 0; q < 8; q++) x[q] = __ldg(pt_lane + c[q] * (uint32_t)Iw);
+    hs8(pl, x);
+    inbatch += 8;
+    if (inbatch > sparse::FLUSH_AT || i + 8 >= plen) {
+      flush_planes(c16, pl, bits_for(inbatch));
+      inbatch = 0;
+    }
+  }
+  uint4* out = reinterpret_cast<uint4*>(pcnt) + (size_t)w * 128 + lane;
+#pragma unroll
+  for (int q = 0; q < 4; q++) out[q * 32] = make_uint4(c16[4 * q], c16[4 * q + 1], c16[4 * q + 2], c16[4 * q + 3]);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // CT = carrier index type of the list views: uint16_t (n <= 65,535) or uint32_t
-template <int M, bool KEEP, typename CT>
+template <int M, bool KEEP, typename CT, bool PC>
 __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_sparse_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse;
   const CT* car0 = static_cast<const CT*>(s.car0);
@@ -239,11 +302,19 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     const uint32_t* pt_lane = a.pt + pb * 32 + lane;
     const uint64_t* p0row = a.p0 + (size_t)idx * row_words;
     const uint32_t loc0 = a.location[idx];
+    // PC: pull the pre-counted rows of a partner (2 KB per half and permutation block = 16 lines, one per lane) towards
+    // the SM ahead of their use - the table is far larger than L2 and each row is read once per pair
+    auto prefetch_partner = [&](uint32_t loc) {
+      if (lane < 16 * M)
+        prefetch_l2(reinterpret_cast<const char*>(s.pcnt1) + (((size_t)loc * M + (lane >> 4)) * s.n_perm_blocks + pb) * 2048 + (lane & 15) * 128);
+    };
+    if (PC && j0 < j1) prefetch_partner(loc0 + j0);
 
     uint32_t pl[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) pl[j] = 0;
-    int inbatch = 0;
+    int inbatch = 0;  // carrier slots (sentinels included) in the planes
+    int inreal = 0;   // upper bound of the count any permutation can have reached in the planes: sets how many planes a flush reads
 
     // add eight carriers of a list (sentinel entries hit the zero row) to the bit planes
     // `last`: nothing more will be added to these counters - flush what the planes hold.  The overflow flush (planes
@@ -256,14 +327,15 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       for (int q = 0; q < 8; q++) x[q] = __ldg(pt_lane + c[q] * (uint32_t)Iw);
       hs8(pl, x);
       inbatch += 8;
+      inreal += 8;
       if (inbatch > FLUSH_AT || last) {
-        flush_planes(c16, pl, bits_for(inbatch));
-        inbatch = 0;
+        flush_planes(c16, pl, bits_for(inreal));
+        inbatch = inreal = 0;
       }
     };
 
     // the same for eight pre-multiplied row offsets (filtered partner carriers, multiplied once per lane in the filter)
-    auto add8_off = [&](uint32_t (&c16)[16], const uint4 lo, const uint4 hi, bool last) {
+    auto add8_off = [&](uint32_t (&c16)[16], const uint4 lo, const uint4 hi, int real, bool last) {
       uint32_t x[8];
       x[0] = __ldg(pt_lane + lo.x);
       x[1] = __ldg(pt_lane + lo.y);
@@ -275,9 +347,10 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       x[7] = __ldg(pt_lane + hi.w);
       hs8(pl, x);
       inbatch += 8;
+      inreal += real;
       if (inbatch > FLUSH_AT || last) {
-        flush_planes(c16, pl, bits_for(inbatch));
-        inbatch = 0;
+        flush_planes(c16, pl, bits_for(inreal));
+        inbatch = inreal = 0;
       }
     };
 
@@ -287,17 +360,29 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     for (int h = 0; h < M; h++) t0[h] = nc0[h] = 0;
 #pragma unroll 1
     for (int h = 0; h < M; h++) {
-      uint32_t acc[16];
-#pragma unroll
-      for (int i = 0; i < 16; i++) acc[i] = 0;
       const size_t item = (size_t)idx * M + h;
-      const uint32_t o = s.off0[item], plen = s.off0[item + 1] - o;
       const uint32_t t0h = s.len0[item], nc0h = s.ncase0[item];
       if (M == 1 || h == 0) { t0[0] = t0h; nc0[0] = nc0h; } else { t0[M - 1] = t0h; nc0[M - 1] = nc0h; }
-#pragma unroll 1
-      for (uint32_t i = 0; i < plen; i += 8) add8(acc, car0 + o + i, i + 8 >= plen);
+      if (s.pcnt0) {  // counts emitted by the join that produced the upstream rows
+        const uint4* B = reinterpret_cast<const uint4*>(s.pcnt0) + ((item * s.n_perm_blocks + pb) * 4) * 32 + lane;
 #pragma unroll
-      for (int i = 0; i < 16; i++) s_base[warp][h][i][lane] = acc[i];
+        for (int q = 0; q < 4; q++) {
+          const uint4 v = __ldg(B + q * 32);
+          s_base[warp][h][4 * q][lane] = v.x;
+          s_base[warp][h][4 * q + 1][lane] = v.y;
+          s_base[warp][h][4 * q + 2][lane] = v.z;
+          s_base[warp][h][4 * q + 3][lane] = v.w;
+        }
+      } else {
+        uint32_t acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = 0;
+        const uint32_t o = s.off0[item], plen = s.off0[item + 1] - o;
+#pragma unroll 1
+        for (uint32_t i = 0; i < plen; i += 8) add8(acc, car0 + o + i, i + 8 >= plen);
+#pragma unroll
+        for (int i = 0; i < 16; i++) s_base[warp][h][i][lane] = acc[i];
+      }
     }
     __syncwarp();
 
@@ -305,16 +390,18 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     // ---- partners ----
     for (uint32_t j = j0; j < j1; j++) {
       const uint32_t loc = loc0 + j;
+      if (PC && j + 1 < j1) prefetch_partner(loc + 1);
       bool flip = true;
       if (M == 2) flip = need_flip(a.path_length, a.signs, idx, loc);
-      uint32_t c16[16];          // counts of the half being accumulated
-      uint32_t nd[M], ncn[M];
+      uint32_t c16[16];          // counts of the half being accumulated (PC: of up & partner only)
+      uint32_t nd[M], ncn[M];    // carriers / case carriers the partner adds to the upstream half
+      size_t pitem[M];           // PC: the partner item joined into half h
 #pragma unroll
-      for (int h = 0; h < M; h++) nd[h] = ncn[h] = 0;
+      for (int h = 0; h < M; h++) { nd[h] = ncn[h] = 0; pitem[h] = 0; }
 #pragma unroll 1
       for (int h = 0; h < M; h++) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) c16[i] = s_base[warp][h][i][lane];
+        for (int i = 0; i < 16; i++) c16[i] = PC ? 0u : s_base[warp][h][i][lane];
         // joined half h = upstream half h | partner half hh   (src/methods.h:137-145)
         const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
         const size_t item = (size_t)loc * M + hh;
@@ -328,7 +415,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           const bool valid = i < len;
           const uint32_t c = valid ? (uint32_t)car1[o + i] : 0u;
           const uint32_t w0 = valid ? __ldg(reinterpret_cast<const uint32_t*>(p0h) + (c >> 5)) : 0u;
-          const bool keep = valid && !((w0 >> (c & 31)) & 1u);   // not already a carrier of the upstream row
+          // delta: carriers not yet in the upstream row are added to the base; PC: carriers already in it are subtracted
+          const bool keep = valid && (((w0 >> (c & 31)) & 1u) != 0u) == PC;
           const unsigned km = __ballot_sync(0xffffffffu, keep);
           ncnh += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
           if (keep) queue[qn + __popc(km & lt_mask)] = c * (uint32_t)Iw;
@@ -344,7 +432,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
             __syncwarp();
 #pragma unroll 1
             for (uint32_t q0 = 0; q0 < take; q0 += 8)
-              add8_off(c16, *reinterpret_cast<const uint4*>(queue + q0), *reinterpret_cast<const uint4*>(queue + q0 + 4), last_chunk && q0 + 8 >= take);
+              add8_off(c16, *reinterpret_cast<const uint4*>(queue + q0), *reinterpret_cast<const uint4*>(queue + q0 + 4),
+                       (int)min(8u, qn > q0 ? qn - q0 : 0u), last_chunk && q0 + 8 >= take);
             const uint32_t rem = last_chunk ? 0u : qn - 64u;
             const uint32_t keepv = (lane < rem) ? queue[64 + lane] : 0u;
             __syncwarp();
@@ -353,13 +442,18 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
             qn = rem;
           }
         }
+        if (PC) {  // what the filter kept is the overlap: added = partner - overlap
+          ndh = len - ndh;
+          ncnh = s.ncase1[item] - ncnh;
+        }
         if (M == 2) {
 #pragma unroll
           for (int i = 0; i < 16; i++) s_cnt[warp][h][i][lane] = c16[i];
-          if (h == 0) { nd[0] = ndh; ncn[0] = ncnh; } else { nd[M - 1] = ndh; ncn[M - 1] = ncnh; }
+          if (h == 0) { nd[0] = ndh; ncn[0] = ncnh; pitem[0] = item; } else { nd[M - 1] = ndh; ncn[M - 1] = ncnh; pitem[M - 1] = item; }
         } else {
           nd[0] = ndh;
           ncn[0] = ncnh;
+          pitem[0] = item;
         }
       }
 
@@ -367,7 +461,48 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       if (M == 2) empty = empty && nd[M - 1] == 0;
       if (!empty || !base_done) {
         if (empty) base_done = true;
-        if (M == 1) {
+        if (PC) {
+          // counts = base + P[partner] - overlap, packed u16 pairs (whole-register arithmetic is exact: every final half
+          // is a count in [0, 65535]); register i holds permutation bits b = ((i & 1) * 2 + hf) * 8 + (i >> 1), hf = 0, 1
+          const uint4* P0 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[0] * s.n_perm_blocks + pb) * 4) * 32 + lane;
+          if (M == 1) {
+            const unsigned total = t0[0] + nd[0];
+            const float* row = a.diagF + diag_base(total);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const uint4 pv = __ldg(P0 + q * 32);
+              const uint32_t pr[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int i = 4 * q + k;
+                const uint32_t v = s_base[warp][0][i][lane] + pr[k] - c16[i];
+                best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __ldg(row + (v & 0xffffu)));
+                best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __ldg(row + (v >> 16)));
+              }
+            }
+          } else {
+            const uint4* P1 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[M - 1] * s.n_perm_blocks + pb) * 4) * 32 + lane;
+            const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
+            const double* rowp = a.diagDM + diag_base(tp);
+            const double* rown = a.diagDM + diag_base(tn) + tn;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const uint4 pvp = __ldg(P0 + q * 32), pvn = __ldg(P1 + q * 32);
+              const uint32_t prp[4] = {pvp.x, pvp.y, pvp.z, pvp.w}, prn[4] = {pvn.x, pvn.y, pvn.z, pvn.w};
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int i = 4 * q + k;
+                const uint32_t vp = s_base[warp][0][i][lane] + prp[k] - s_cnt[warp][0][M == 2 ? i : 0][lane];
+                const uint32_t vn = s_base[warp][M - 1][i][lane] + prn[k] - s_cnt[warp][M == 2 ? 1 : 0][M == 2 ? i : 0][lane];
+                // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
+                const double vlo = __ldg(rowp + (vp & 0xffffu)) + __ldg(rown - (vn & 0xffffu));
+                const double vhi = __ldg(rowp + (vp >> 16)) + __ldg(rown - (vn >> 16));
+                best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __double2float_rn(vlo));
+                best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __double2float_rn(vhi));
+              }
+            }
+          }
+        } else if (M == 1) {
           const unsigned total = t0[0] + nd[0];
           const float* row = a.diagF + diag_base(total);
 #pragma unroll
@@ -388,6 +523,25 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
             // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
             const double v = __ldg(rowp + cp) + __ldg(rown - cn);
             best[b] = fmaxf(best[b], __double2float_rn(v));
+          }
+        }
+      }
+
+      if (KEEP && !PC && s.pcnt_res) {
+        // ---- the kept row's counts and carrier totals travel with it (base of the next level) ----
+        const size_t r = (size_t)(a.res_idx[idx] + j);
+#pragma unroll
+        for (int h = 0; h < M; h++) {
+          uint4* out = reinterpret_cast<uint4*>(s.pcnt_res) + (((r * M + h) * s.n_perm_blocks + pb) * 4) * 32 + lane;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (M == 1) out[q * 32] = make_uint4(c16[4 * q], c16[4 * q + 1], c16[4 * q + 2], c16[4 * q + 3]);
+            else out[q * 32] = make_uint4(s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q : 0][lane], s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 1 : 0][lane],
+                                          s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 2 : 0][lane], s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 3 : 0][lane]);
+          }
+          if (first_pb && lane == 0) {
+            s.len_res[r * M + h] = t0[h == 0 ? 0 : M - 1] + nd[h == 0 ? 0 : M - 1];
+            s.ncase_res[r * M + h] = nc0[h == 0 ? 0 : M - 1] + ncn[h == 0 ? 0 : M - 1];
           }
         }
       }
@@ -462,12 +616,19 @@ static inline bool sparse_preferred(int W64, int Ip_dense, int Iw) {
   return (long long)W64 * Ip_dense > 6400ll * (Iw / 32);
 }
 
-template <int M, bool KEEP>
+template <int M, bool KEEP, bool PC>
 static inline void launch_sparse_ct(unsigned grid, cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, bool wide) {
-  if (wide) join_sparse_kernel<M, KEEP, uint32_t><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
-  else join_sparse_kernel<M, KEEP, uint16_t><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+  if (wide) join_sparse_kernel<M, KEEP, uint32_t, PC><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+  else join_sparse_kernel<M, KEEP, uint16_t, PC><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
 }
 
+template <int M, bool KEEP>
+static inline void launch_sparse_pc(unsigned grid, cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, bool wide) {
+  if (sp.pcnt1) launch_sparse_ct<M, KEEP, true>(grid, stream, jp, sp, wide);
+  else launch_sparse_ct<M, KEEP, false>(grid, stream, jp, sp, wide);
+}
+
+// sp.pcnt1 != null selects the pre-counted-partner kernels
 static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count) {
   const unsigned long long n_work = sp.n_units * (unsigned long long)sp.n_perm_blocks;
   if (n_work == 0) return cudaSuccess;
@@ -475,13 +636,27 @@ static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinPara
   const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * sparse::min_blocks(M));
   const bool wide = sparse_wide(sp.n);
   if (M == 1) {
-    if (keep) launch_sparse_ct<1, true>(grid, stream, jp, sp, wide);
-    else launch_sparse_ct<1, false>(grid, stream, jp, sp, wide);
+    if (keep) launch_sparse_pc<1, true>(grid, stream, jp, sp, wide);
+    else launch_sparse_pc<1, false>(grid, stream, jp, sp, wide);
   } else {
-    if (keep) launch_sparse_ct<2, true>(grid, stream, jp, sp, wide);
-    else launch_sparse_ct<2, false>(grid, stream, jp, sp, wide);
+    if (keep) launch_sparse_pc<2, true>(grid, stream, jp, sp, wide);
+    else launch_sparse_pc<2, false>(grid, stream, jp, sp, wide);
   }
   return cudaGetLastError();
+}
+
+// Pre-counted partners replace the walk over the partner's new carriers by a 2 KB read plus a walk over the carriers
+// the two rows SHARE.  In the level schedule of the reference a partner path always starts at the gene the upstream path
+// ends in, so the shared part is about as long as the new part and the form loses (BASELINE config 3, ms per launch,
+// delta / pre-counted: level 4 method 1 13.1 / 15.0, method 2 22.4 / 27.0; level 5 147 / 123 and 244 / 242; level 3, where
+// the partners are single genes, 2.7 / 2.4 and 5.8 / 5.8).  It is therefore opt-in: GCRE_PRECOUNT=1 (GCRE_TEST_PRECOUNT
+// in the tests) selects it for joins whose table fits the budget.
+static inline bool precount_preferred(unsigned long long pairs, unsigned long long partner_rows, int M, int n_perm_blocks, size_t budget_bytes) {
+  if (partner_rows == 0 || pairs == 0) return false;
+  if ((size_t)partner_rows * M * n_perm_blocks * 2048 > budget_bytes) return false;
+  const char* f = std::getenv("GCRE_TEST_PRECOUNT");
+  if (!f) f = std::getenv("GCRE_PRECOUNT");
+  return f && *f == '1';
 }
 
 }  // namespace gcre

@@ -82,6 +82,8 @@ typedef struct {
   double kernel_ms;         /* out: device time of the join kernels of this call (CUDA events) */
   int32_t kernel_used;      /* out: gcre_kernel actually run */
   int32_t launches;         /* out: kernel launches made by this call */
+  int32_t precounted;       /* out: 1 when the sparse kernel ran in its pre-counted-partner form (join_sparse.cuh) */
+  int32_t reserved;
 } gcre_join_opts;
 
 const char* gcre_last_error(void);

@@ -13,7 +13,29 @@ from test_oracle import GOLDENS, _kat, check_kat
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [_lib.KERNEL_DENSE, _lib.KERNEL_SPARSE]
+
+
+class _Precount(int):
+    """KERNEL_SPARSE with the pre-counted-partner kernels forced on (GCRE_TEST_PRECOUNT=1); plain KERNEL_SPARSE forces the
+    delta kernels, so both families run on every shape whatever the cost model would pick."""
+
+
+SPARSE_PC = _Precount(_lib.KERNEL_SPARSE)
+KERNELS = [pytest.param(_lib.KERNEL_DENSE, id="dense"), pytest.param(_lib.KERNEL_SPARSE, id="sparse"), pytest.param(SPARSE_PC, id="sparse_pc")]
+PC_MODES = [pytest.param("0", id="delta"), pytest.param("1", id="precount")]
+
+
+@pytest.fixture(autouse=True)
+def _precount_mode(request, monkeypatch):
+    params = getattr(getattr(request.node, "callspec", None), "params", {})
+    k = params.get("kernel")
+    if isinstance(k, _Precount):
+        monkeypatch.setenv("GCRE_TEST_PRECOUNT", "1")
+    elif k == _lib.KERNEL_SPARSE:
+        monkeypatch.setenv("GCRE_TEST_PRECOUNT", "0")
+    if "pc" in params:
+        monkeypatch.setenv("GCRE_TEST_PRECOUNT", params["pc"])
+
 
 
 def run_engine(engine, w, method, path_length, top_k, kernel, **kw):
@@ -67,6 +89,27 @@ def test_schedule_matches_oracle(engine, oracles, method, shape, kernel):
     for lvl in want:
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} {shape} L{lvl}")
         assert got[lvl].info["kernel"] == kernel, "the requested kernel family must be the one that ran"
+        if kernel == _lib.KERNEL_SPARSE and w.net.levels[lvl].n_pairs > 0 and lvl in ("1b", "4", "5"):
+            # (joins that keep their rows emit the rows' counts for the next level instead, in the delta form)
+            assert got[lvl].info["precounted"] == isinstance(kernel, _Precount), "GCRE_TEST_PRECOUNT must select the kernel form"
+
+
+@pytest.mark.parametrize("pc", PC_MODES)
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_schedule_without_emitted_counts(engine, oracles, method, pc, monkeypatch):
+    """By default a KEEP join hands the per-permutation counts of its rows to the next level (which then needs no carrier
+    lists of its upstream operand); GCRE_TEST_EMIT=0 turns that off, so the in-kernel base walk and - with pre-counting
+    forced - the KEEP form of the pre-counted kernels run on the full schedule too."""
+    monkeypatch.setenv("GCRE_TEST_EMIT", "0")
+    shape = SHAPES[4]
+    nc, nt, g, e, perms, top_k = shape
+    w = synth.make_workload(nc, nt, g, e, perms, seed=4242, max_path_length=5, real_table=True, max_freq=0.12, zero_frac=0.3)
+    want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 5, top_k)
+    got, kept, _ = run_engine(engine, w, method, 5, top_k, _lib.KERNEL_SPARSE)
+    for k in kept_want:
+        assert np.array_equal(kept[k], kept_want[k]), f"kept {k} differs"
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
 
 
 @pytest.mark.parametrize("method", ["method1", "method2"])
@@ -279,8 +322,9 @@ def test_dense_carrier_rows(engine, oracles, method, kernel):
         assert got[lvl].info["kernel"] == kernel
 
 
+@pytest.mark.parametrize("pc", PC_MODES)
 @pytest.mark.parametrize("method", ["method1", "method2"])
-def test_wide_carrier_indices(engine, oracles, method, monkeypatch):
+def test_wide_carrier_indices(engine, oracles, method, pc, monkeypatch):
     """Cohorts above 65,535 patients use 32-bit carrier indices in the sparse kernel's lists; GCRE_TEST_WIDE_CARRIERS
     forces that code path on a cohort the oracle can check."""
     monkeypatch.setenv("GCRE_TEST_WIDE_CARRIERS", "1")
@@ -333,8 +377,9 @@ def test_resident_join_index_matches_one_shot(engine):
         assert ra.info["pairs"] == rb.info["pairs"] > 0
 
 
+@pytest.mark.parametrize("pc", PC_MODES)
 @pytest.mark.parametrize("method", ["method1", "method2"])
-def test_sparse_queue_drain_corner_cases(engine, oracles, method):
+def test_sparse_queue_drain_corner_cases(engine, oracles, method, pc):
     """Hand-built rows that hit the carrier-queue edge cases of the sparse kernel: exactly 64 new carriers followed by list
     entries that are all already in the upstream row (a mid-list drain, then nothing left to drain but counts still in the
     bit planes), 65 new carriers, and a partner that adds nothing."""
