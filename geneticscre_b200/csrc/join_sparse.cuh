@@ -48,10 +48,15 @@ constexpr int QCAP = 96;        // per-warp queue of filtered partner carriers (
 // (12 M pairs, ms per launch): method 1: 4 CTAs (128 regs) 19.9, 5: 17.4, 6: 16.2, 8 (64 regs, 164 B spilled) 15.0;
 // method 2: 4: 33.9, 5: 39.1, 6: 40.2, 8: 40.0.  Keeping the per-permutation state in shared memory instead (no
 // spills at 48 regs, 1,000 SASS instructions) was slower for both (22 / 35 ms): the kernel is issue-bound.
+// Method 2 again after its two halves were rolled into one loop (counts parked in shared memory): 4 CTAs (128 regs) 20.2 ms,
+// 5 (96 regs, no spills) 19.0, 6 (80 regs, 84 B spilled) 26.4.
 #ifndef GCRE_SPARSE_MB2
-#define GCRE_SPARSE_MB2 4
+#define GCRE_SPARSE_MB2 5
 #endif
-constexpr int min_blocks(int m) { return m == 1 ? 8 : GCRE_SPARSE_MB2; }
+#ifndef GCRE_SPARSE_MB1
+#define GCRE_SPARSE_MB1 8
+#endif
+constexpr int min_blocks(int m) { return m == 1 ? GCRE_SPARSE_MB1 : GCRE_SPARSE_MB2; }
 }  // namespace sparse
 
 // Carrier-list (CSR) view of a path set: per (row, half) the ascending patient indices of its set bits.
@@ -335,8 +340,9 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     };
 
     // the same for eight pre-multiplied row offsets (filtered partner carriers, multiplied once per lane in the filter)
-    auto add8_off = [&](uint32_t (&c16)[16], const uint4 lo, const uint4 hi, int real, bool last) {
-      uint32_t x[8];
+    // (keeping a second group of gathers in flight while the first is added - method 2 has the registers - gained < 1 %)
+    auto gather8 = [&](uint32_t (&x)[8], const uint32_t* q8) {
+      const uint4 lo = *reinterpret_cast<const uint4*>(q8), hi = *reinterpret_cast<const uint4*>(q8 + 4);
       x[0] = __ldg(pt_lane + lo.x);
       x[1] = __ldg(pt_lane + lo.y);
       x[2] = __ldg(pt_lane + lo.z);
@@ -345,6 +351,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       x[5] = __ldg(pt_lane + hi.y);
       x[6] = __ldg(pt_lane + hi.z);
       x[7] = __ldg(pt_lane + hi.w);
+    };
+    auto acc8 = [&](uint32_t (&c16)[16], const uint32_t (&x)[8], int real, bool last) {
       hs8(pl, x);
       inbatch += 8;
       inreal += real;
@@ -431,9 +439,11 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
             if (last_chunk && lane < take - qn) queue[qn + lane] = (uint32_t)s.n * (uint32_t)Iw;
             __syncwarp();
 #pragma unroll 1
-            for (uint32_t q0 = 0; q0 < take; q0 += 8)
-              add8_off(c16, *reinterpret_cast<const uint4*>(queue + q0), *reinterpret_cast<const uint4*>(queue + q0 + 4),
-                       (int)min(8u, qn > q0 ? qn - q0 : 0u), last_chunk && q0 + 8 >= take);
+            for (uint32_t q0 = 0; q0 < take; q0 += 8) {
+              uint32_t x[8];
+              gather8(x, queue + q0);
+              acc8(c16, x, (int)min(8u, qn > q0 ? qn - q0 : 0u), last_chunk && q0 + 8 >= take);
+            }
             const uint32_t rem = last_chunk ? 0u : qn - 64u;
             const uint32_t keepv = (lane < rem) ? queue[64 + lane] : 0u;
             __syncwarp();
