@@ -69,6 +69,12 @@ struct JoinParams {
   unsigned* cand_count;
   unsigned cand_cap;
   unsigned long long thr_key;  // append candidates whose key is strictly greater
+  // Self-tightening threshold (sparse kernels, top_k <= 64).  slots[n_slots = top_k] hold, per hash bucket of (idx, loc),
+  // the largest key appended so far; once every bucket is filled there are top_k distinct pairs with key >= min(slots),
+  // so a pair strictly below that minimum cannot be in the top K.  dyn_thr caches the minimum (0 = not yet known).
+  unsigned long long* dyn_thr;
+  unsigned long long* slots;
+  int n_slots;
   unsigned* max_total;     // atomicMax of per-half carrier totals of kept rows
 };
 

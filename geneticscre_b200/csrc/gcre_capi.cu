@@ -215,6 +215,7 @@ struct gcre_exec {
   long long diag_cap = -1;
   // outputs / scratch
   int* d_perm_max = nullptr;
+  unsigned long long* d_topk = nullptr;  // [0] self-tightening candidate threshold, [1..64] its hash-bucket maxima (JoinParams::slots)
   unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total, [2..3] 64-bit work counter of the sparse kernel
   DevBuf cand, scratch, scan_tmp;
   unsigned* h_scalars = nullptr;  // pinned
@@ -367,6 +368,7 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
     CK(cudaMemsetAsync(ex->d_pm, 0, (size_t)ex->Wp * ex->Ip * 8, ex->stream));
     CK(dev_alloc(ex, (void**)&ex->d_perm_max, (size_t)ex->Ip * 4));
     CK(cudaMemsetAsync(ex->d_perm_max, 0, (size_t)ex->Ip * 4, ex->stream));
+    CK(dev_alloc(ex, (void**)&ex->d_topk, 65 * sizeof(unsigned long long)));
     CK(dev_alloc(ex, (void**)&ex->d_scalars, 16 * sizeof(unsigned)));
     CK(cudaMemsetAsync(ex->d_scalars, 0, 16 * sizeof(unsigned), ex->stream));
     CK(cudaMallocHost(&ex->h_scalars, 16 * sizeof(unsigned)));
@@ -387,7 +389,7 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   if (ex->copy_stream) cudaStreamSynchronize(ex->copy_stream);
   reap_staged(ex, true);
   for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
-                  (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars})
+                  (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk})
     dev_free(ex, p);
   if (ex->h_scalars) cudaFreeHost(ex->h_scalars);
   ex->cand.release();
@@ -1291,6 +1293,12 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   jp.perm_max = ex->d_perm_max;
   jp.cand_count = ex->d_scalars;
   jp.max_total = ex->d_scalars + 1;
+  if (kernel == GCRE_KERNEL_SPARSE && top_k <= 64) {
+    CK(cudaMemsetAsync(ex->d_topk, 0, 65 * sizeof(unsigned long long), ex->stream));
+    jp.dyn_thr = ex->d_topk;
+    jp.slots = ex->d_topk + 1;
+    jp.n_slots = top_k;
+  }
 
   // ---- chunked launches; candidates merged on the host between chunks ----
   // dense kernel: chunks are ranges of flattened pairs; sparse kernel: ranges of units (<= PB pairs each)
@@ -1300,7 +1308,9 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   // Launch plan.  Top-K candidates are appended by the kernels only when their score beats the K-th best known so far,
   // and a launch must be able to hold every candidate it may produce:
   //   * small joins (<= 64K pairs): one launch with room for every pair;
-  //   * large joins: a short prefix (threshold unknown: every pair is a candidate) establishes the K-th score, then
+  //   * large joins, sparse kernel, top_k <= 64: ONE launch with the fixed candidate budget - the kernel raises its own
+  //     threshold as candidates arrive (JoinParams::slots; measured: ~300 candidates out of 12 M pairs);
+  //   * other large joins: a short prefix (threshold unknown: every pair is a candidate) establishes the K-th score, then
   //     ONE launch covers the rest with a fixed candidate budget.  Pairs are visited in ascending (src, trg) order
   //     across launches, so later pairs only displace on a strictly greater score.  If the budget overflows (scores that
   //     keep rising), that launch's candidates are dropped and the range is redone in safe chunks (cap = chunk size);
@@ -1316,6 +1326,9 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   const unsigned long long redo_max = std::max<unsigned long long>(1, (tiny_plan ? 512ull : (4ull << 20)) / per_item);
   if (item_hi - item_lo <= small_items) {
     if (item_hi > item_lo) plan.push_back({item_lo, item_hi, true});
+  } else if (jp.n_slots > 0) {
+    // the kernel tightens its own threshold (JoinParams::slots): no prefix launch needed, a few hundred candidates in all
+    plan.push_back({item_lo, item_hi, false});
   } else {
     plan.push_back({item_lo, item_lo + prefix_items, true});
     plan.push_back({item_lo + prefix_items, item_hi, false});
@@ -1367,6 +1380,12 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
       continue;
     }
     const unsigned n_cand = ex->h_scalars[0];
+    if (tr.on) {
+      char buf[96];
+      snprintf(buf, sizeof buf, " [launch %llu..%llu cand=%u %.3fms]", p, pe, n_cand, ms);
+      tr.line += buf;
+      tr.mark("run");
+    }
     if (n_cand) {
       h_cand.resize(n_cand);
       CK(cudaMemcpyAsync(h_cand.data(), ex->cand.p, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, ex->stream));
@@ -1388,6 +1407,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
         thr_key = score_key(kth);
       }
     }
+    tr.mark("cands");
   }
   tr.mark("launches");
   if (keep) {

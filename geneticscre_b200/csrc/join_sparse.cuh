@@ -592,12 +592,21 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           if (KEEP) atomicMax(a.max_total, tmax);
           if (score == score) {
             const unsigned long long key = score_key(score);
-            if (key > a.thr_key) {
+            const unsigned long long dyn = a.n_slots ? __ldcg(a.dyn_thr) : 0ull;  // (read here, by lane 0 only: no register held across the pair)
+            if (key > a.thr_key && key >= dyn) {
               const unsigned slot = atomicAdd(a.cand_count, 1u);
               if (slot < a.cand_cap) {
                 Cand cd;
                 cd.key = key; cd.idx = idx; cd.loc = loc; cd.cases = cases; cd.ctrls = ctrls;
                 a.cand[slot] = cd;
+              }
+              if (a.n_slots) {
+                const unsigned bucket = ((idx * 0x9E3779B1u) ^ (loc * 0x85EBCA6Bu)) >> 8;
+                if (atomicMax(a.slots + bucket % (unsigned)a.n_slots, key) < key) {
+                  unsigned long long m = ~0ull;
+                  for (int t = 0; t < a.n_slots; t++) m = min(m, __ldcg(a.slots + t));
+                  if (m > dyn) atomicMax(a.dyn_thr, m);
+                }
               }
             }
           }

@@ -255,8 +255,10 @@ def test_pathset_row_access(engine):
 
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("method", ["method1", "method2"])
-def test_topk_launch_plan_paths(engine, oracles, method, kernel, monkeypatch):
-    """Prefix launch, fixed candidate budget, budget overflow and the safe redo give the same top-K and maxima.
+@pytest.mark.parametrize("top_k", [9, 70])
+def test_topk_launch_plan_paths(engine, oracles, method, kernel, top_k, monkeypatch):
+    """Prefix launch, fixed candidate budget, budget overflow and the safe redo give the same top-K and maxima
+    (top_k <= 64 on the sparse kernel: one launch with the self-tightening threshold instead of the prefix).
 
     GCRE_TEST_SMALL_PLAN shrinks the plan sizes so a few-thousand-pair join takes every path; the value table rises
     with the carrier count, which makes late pairs keep beating the threshold (the overflow case)."""
@@ -264,8 +266,8 @@ def test_topk_launch_plan_paths(engine, oracles, method, kernel, monkeypatch):
     w = synth.make_workload(80, 85, 160, 700, 33, seed=31, max_path_length=4, real_table=False, max_freq=0.15, zero_frac=0.2)
     i, j = np.meshgrid(np.arange(w.n_cases + 1), np.arange(w.n_ctrls + 1), indexing="ij")
     w.value_table = (i * 1.0 + j * 0.5 + ((i * 7 + j * 3) % 5) * 0.01).astype(np.float64)
-    want, _, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, 9)
-    got, _, _ = run_engine(engine, w, method, 4, 9, kernel)
+    want, _, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, top_k)
+    got, _, _ = run_engine(engine, w, method, 4, top_k, kernel)
     for lvl in want:
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
     assert got["4"].info["launches"] >= 3
