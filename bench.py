@@ -473,7 +473,7 @@ def main():
                 "note": "HBM fraction reported per contract; the dense kernel is bound by the INT/XU (POPC) pipe (96 % utilised, profiles/r1_dense_full.txt); "
                         "the sparse kernel skips work the algorithmic figure still counts (carrier lists instead of all W words; DRAM traffic far below the "
                         "algorithmic bytes), so int_frac_nominal > 1 is its algorithmic speed-up over the dense roof, not a utilisation - it is issue/ALU-bound "
-                        "(71 % issue slots active, ALU pipe 75 %, profiles/r1_sparse_m1_level4_full.txt)"}
+                        "(55-73 % issue slots active, ALU the top pipe, profiles/r1_sparse_r1final_level4_full.txt)"}
 
     # ---- the metric per level as well as in aggregate (kernel time of each join, CUDA events inside gcre_join) ----
     per_level = None

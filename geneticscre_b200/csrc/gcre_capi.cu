@@ -796,7 +796,13 @@ extern "C" int gcre_pathset_select(const gcre_pathset* ps, const int32_t* indice
       return rc;
     }
   }
-  res->max_half_pop = ps->max_half_pop;  // an upper bound is all that is needed
+  // an upper bound is all a join needs: the source's maximum, computed once and reused by every selection from it
+  long long src_max = 0;
+  if (n && pathset_max_half_pop(const_cast<gcre_pathset*>(ps), &src_max) != GCRE_OK) {
+    gcre_pathset_destroy(res);
+    return GCRE_ERR_CUDA;
+  }
+  res->max_half_pop = n ? src_max : 0;
   *out = res;
   return GCRE_OK;
 }
