@@ -186,6 +186,68 @@ struct DevBuf {  // grow-only device scratch owned by one exec
   }
 };
 
+// Process-wide pools of the small driver objects an exec needs.  Creating and freeing them per exec (page-locked host
+// words: ~1 ms for cudaMallocHost, ~0.4 ms for cudaFreeHost; streams, events) was most of the 3-5 ms a vignette-sized run
+// took end to end (tools/vignette_breakdown.py); an R session makes one JoinExec per GWASPA() call.
+struct HostPools {
+  std::mutex mu;
+  std::vector<unsigned*> pinned;                              // 16-word page-locked blocks (any device)
+  std::map<int, std::vector<cudaStream_t>> streams;           // per device, non-blocking
+  std::map<int, std::vector<cudaEvent_t>> timing_events, plain_events;
+};
+static HostPools g_pools;
+
+static cudaError_t pool_pinned(unsigned** out) {
+  {
+    std::lock_guard<std::mutex> lock(g_pools.mu);
+    if (!g_pools.pinned.empty()) {
+      *out = g_pools.pinned.back();
+      g_pools.pinned.pop_back();
+      return cudaSuccess;
+    }
+  }
+  return cudaMallocHost(out, 16 * sizeof(unsigned));
+}
+static void unpool_pinned(unsigned* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_pools.mu);
+  g_pools.pinned.push_back(p);
+}
+static cudaError_t pool_stream(int device, cudaStream_t* out) {
+  {
+    std::lock_guard<std::mutex> lock(g_pools.mu);
+    auto& v = g_pools.streams[device];
+    if (!v.empty()) {
+      *out = v.back();
+      v.pop_back();
+      return cudaSuccess;
+    }
+  }
+  return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+static void unpool_stream(int device, cudaStream_t st) {  // the caller has drained it
+  if (!st) return;
+  std::lock_guard<std::mutex> lock(g_pools.mu);
+  g_pools.streams[device].push_back(st);
+}
+static cudaError_t pool_event(int device, bool timing, cudaEvent_t* out) {
+  {
+    std::lock_guard<std::mutex> lock(g_pools.mu);
+    auto& v = (timing ? g_pools.timing_events : g_pools.plain_events)[device];
+    if (!v.empty()) {
+      *out = v.back();
+      v.pop_back();
+      return cudaSuccess;
+    }
+  }
+  return timing ? cudaEventCreate(out) : cudaEventCreateWithFlags(out, cudaEventDisableTiming);
+}
+static void unpool_event(int device, bool timing, cudaEvent_t ev) {
+  if (!ev) return;
+  std::lock_guard<std::mutex> lock(g_pools.mu);
+  (timing ? g_pools.timing_events : g_pools.plain_events)[device].push_back(ev);
+}
+
 struct gcre_exec {
   int M = 1, n_cases = 0, n_ctrls = 0, n = 0, W64 = 0, Wp = 0, iters = 0, Ip = 0, Iw = 0, device = 0, sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -352,15 +414,15 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
   int rc = [&]() -> int {
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&ex->sm_count, cudaDevAttrMultiProcessorCount, device));
-    CK(cudaStreamCreateWithFlags(&ex->own_stream, cudaStreamNonBlocking));
+    CK(pool_stream(device, &ex->own_stream));
     ex->stream = ex->own_stream;
-    CK(cudaEventCreate(&ex->ev0));
-    CK(cudaEventCreate(&ex->ev1));
-    CK(cudaEventCreateWithFlags(&ex->ev_piece, cudaEventDisableTiming));
-    for (auto& e : ex->ev_half) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&ex->copy_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&ex->ev_copy, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ex->ev_order, cudaEventDisableTiming));
+    CK(pool_event(device, true, &ex->ev0));
+    CK(pool_event(device, true, &ex->ev1));
+    CK(pool_event(device, false, &ex->ev_piece));
+    for (auto& e : ex->ev_half) CK(pool_event(device, false, &e));
+    CK(pool_stream(device, &ex->copy_stream));
+    CK(pool_event(device, false, &ex->ev_copy));
+    CK(pool_event(device, false, &ex->ev_order));
     for (DevBuf* b : {&ex->cand, &ex->scratch, &ex->scan_tmp}) b->owner = ex;
     CK(dev_alloc(ex, (void**)&ex->d_masks, std::max<size_t>((size_t)iters * ex->W64, 1) * 8));
     CK(dev_alloc(ex, (void**)&ex->d_pm, (size_t)ex->Wp * ex->Ip * 8));
@@ -371,7 +433,7 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
     CK(dev_alloc(ex, (void**)&ex->d_topk, 65 * sizeof(unsigned long long)));
     CK(dev_alloc(ex, (void**)&ex->d_scalars, 16 * sizeof(unsigned)));
     CK(cudaMemsetAsync(ex->d_scalars, 0, 16 * sizeof(unsigned), ex->stream));
-    CK(cudaMallocHost(&ex->h_scalars, 16 * sizeof(unsigned)));
+    CK(pool_pinned(&ex->h_scalars));
     return GCRE_OK;  // no host sync: everything later is ordered on ex->stream (gcre_exec_set_stream carries the order over)
   }();
   if (rc != GCRE_OK) {
@@ -391,18 +453,19 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
                   (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk})
     dev_free(ex, p);
-  if (ex->h_scalars) cudaFreeHost(ex->h_scalars);
   ex->cand.release();
   ex->scan_tmp.release();
   ex->scratch.release();
-  if (ex->ev0) cudaEventDestroy(ex->ev0);
-  if (ex->ev1) cudaEventDestroy(ex->ev1);
-  if (ex->ev_piece) cudaEventDestroy(ex->ev_piece);
-  for (auto e : ex->ev_half) if (e) cudaEventDestroy(e);
-  if (ex->ev_copy) cudaEventDestroy(ex->ev_copy);
-  if (ex->ev_order) cudaEventDestroy(ex->ev_order);
-  if (ex->copy_stream) cudaStreamDestroy(ex->copy_stream);
-  if (ex->own_stream) cudaStreamDestroy(ex->own_stream);
+  // streams (drained above), events and the page-locked words go back to the process-wide pools
+  unpool_pinned(ex->h_scalars);
+  unpool_event(ex->device, true, ex->ev0);
+  unpool_event(ex->device, true, ex->ev1);
+  unpool_event(ex->device, false, ex->ev_piece);
+  for (auto e : ex->ev_half) unpool_event(ex->device, false, e);
+  unpool_event(ex->device, false, ex->ev_copy);
+  unpool_event(ex->device, false, ex->ev_order);
+  unpool_stream(ex->device, ex->copy_stream);
+  unpool_stream(ex->device, ex->own_stream);
   delete ex;
   return GCRE_OK;
 }
