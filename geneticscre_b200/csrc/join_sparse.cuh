@@ -545,9 +545,9 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           uint4* out = reinterpret_cast<uint4*>(s.pcnt_res) + (((r * M + h) * s.n_perm_blocks + pb) * 4) * 32 + lane;
 #pragma unroll
           for (int q = 0; q < 4; q++) {
-            if (M == 1) out[q * 32] = make_uint4(c16[4 * q], c16[4 * q + 1], c16[4 * q + 2], c16[4 * q + 3]);
-            else out[q * 32] = make_uint4(s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q : 0][lane], s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 1 : 0][lane],
-                                          s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 2 : 0][lane], s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 3 : 0][lane]);
+            if (M == 1) __stcs(out + q * 32, make_uint4(c16[4 * q], c16[4 * q + 1], c16[4 * q + 2], c16[4 * q + 3]));
+            else __stcs(out + q * 32, make_uint4(s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q : 0][lane], s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 1 : 0][lane],
+                                          s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 2 : 0][lane], s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 3 : 0][lane]));
           }
           if (first_pb && lane == 0) {
             s.len_res[r * M + h] = t0[h == 0 ? 0 : M - 1] + nd[h == 0 ? 0 : M - 1];
@@ -559,14 +559,20 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       if (first_pb) {
         // ---- kept joined row (src/join_base.cpp:246-249) ----
         if (KEEP) {
-          const uint64_t* p1row = a.p1 + (size_t)loc * row_words;
-          uint64_t* out = a.pres + (size_t)(a.res_idx[idx] + j) * row_words;
-          for (int k = lane; k < Wp; k += 32) {
-            if (M == 1) {
-              out[k] = p0row[k] | p1row[k];
-            } else {
-              out[k] = p0row[k] | p1row[(flip ? 0 : Wp) + k];
-              out[Wp + k] = p0row[Wp + k] | p1row[(flip ? Wp : 0) + k];
+          // 16-byte accesses (Wp is even, rows are 16-byte aligned), streaming stores: the row is next read by the following
+          // level's join.  At 100,000 patients a row is 12.5 KB per half and this copy is most of a KEEP join.
+          const ulonglong2* u = reinterpret_cast<const ulonglong2*>(p0row);
+          const ulonglong2* v = reinterpret_cast<const ulonglong2*>(a.p1 + (size_t)loc * row_words);
+          ulonglong2* out = reinterpret_cast<ulonglong2*>(a.pres + (size_t)(a.res_idx[idx] + j) * row_words);
+          const int Wv = Wp >> 1;
+          const int vpos = (M == 2 && !flip) ? Wv : 0, vneg = (M == 2 && !flip) ? 0 : Wv;  // partner half joined into pos / neg
+#pragma unroll 4
+          for (int k = lane; k < Wv; k += 32) {
+            const ulonglong2 x = u[k], y = __ldg(v + vpos + k);
+            __stcs(out + k, make_ulonglong2(x.x | y.x, x.y | y.y));
+            if (M == 2) {
+              const ulonglong2 xn = u[Wv + k], yn = __ldg(v + vneg + k);
+              __stcs(out + Wv + k, make_ulonglong2(xn.x | yn.x, xn.y | yn.y));
             }
           }
         }
