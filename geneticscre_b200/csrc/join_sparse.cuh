@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
         const uint4* B = reinterpret_cast<const uint4*>(s.pcnt0) + ((item * s.n_perm_blocks + pb) * 4) * 32 + lane;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const uint4 v = __ldg(B + q * 32);
+          const uint4 v = __ldcs(B + q * 32);  // read once per unit: keep it from displacing the mask rows in L1
           s_base[warp][h][4 * q][lane] = v.x;
           s_base[warp][h][4 * q + 1][lane] = v.y;
           s_base[warp][h][4 * q + 2][lane] = v.z;
