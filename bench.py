@@ -281,6 +281,9 @@ def main():
     if shard_perms and rank > 0:
         # this rank's own block of permutations (same cohort, network and table on every rank)
         w.perm_masks = synth.make_perm_masks(w.n_cases, w.n_ctrls, w.n_perms, a.seed + 3 + 1000 * rank)
+    # host cores are shared by the ranks of one box: the engine packs int matrices on the host only with >= 8 threads
+    # (gcre_pathset_load_i32), so with several ranks per host it falls back to packing on the device
+    os.environ.setdefault("GCRE_HOST_PACK_THREADS", str(min(16, (os.cpu_count() or 1) // max(world, 1))))
     lv = w.net.levels
     n = w.n_patients
     names = ["1a", "1b", "2", "3", "4", "5"][: a.path_length + 1]

@@ -8,9 +8,9 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libgcre_b200.so")
-SOURCES = [os.path.join(PKG, "csrc", "gcre_capi.cu")]
+SOURCES = [os.path.join(PKG, "csrc", "gcre_capi.cu"), os.path.join(PKG, "csrc", "host_pack.cpp")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
-              "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include")]
+              "-Xcompiler", "-fPIC,-O3,-Wall,-pthread", "-shared", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include")]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
 
 

@@ -186,6 +186,10 @@ struct DevBuf {  // grow-only device scratch owned by one exec
   }
 };
 
+namespace gcre_host {
+void pack_i32_rows(const int32_t* data, size_t rows, int cols, uint64_t* out, size_t out_stride, int threads);  // host_pack.cpp
+}
+
 // Process-wide pools of the small driver objects an exec needs.  Creating and freeing them per exec (page-locked host
 // words: ~1 ms for cudaMallocHost, ~0.4 ms for cudaFreeHost; streams, events) was most of the 3-5 ms a vignette-sized run
 // took end to end (tools/vignette_breakdown.py); an R session makes one JoinExec per GWASPA() call.
@@ -196,6 +200,34 @@ struct HostPools {
   std::map<int, std::vector<cudaEvent_t>> timing_events, plain_events;
 };
 static HostPools g_pools;
+
+// page-locked staging buffers for host-packed uploads (cudaHostAlloc of tens of MB costs milliseconds: allocate once, reuse)
+struct PinnedBlock {
+  void* p;
+  size_t cap;
+};
+static std::vector<PinnedBlock> g_pinned_big;  // guarded by g_pools.mu
+
+static cudaError_t pinned_big_acquire(size_t bytes, PinnedBlock* out) {
+  {
+    std::lock_guard<std::mutex> lock(g_pools.mu);
+    size_t best = g_pinned_big.size();
+    for (size_t i = 0; i < g_pinned_big.size(); i++)
+      if (g_pinned_big[i].cap >= bytes && (best == g_pinned_big.size() || g_pinned_big[i].cap < g_pinned_big[best].cap)) best = i;
+    if (best != g_pinned_big.size()) {
+      *out = g_pinned_big[best];
+      g_pinned_big.erase(g_pinned_big.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  out->cap = bytes + bytes / 8 + 4096;
+  return cudaHostAlloc(&out->p, out->cap, cudaHostAllocDefault);
+}
+static void pinned_big_release(const PinnedBlock& b) {
+  if (!b.p) return;
+  std::lock_guard<std::mutex> lock(g_pools.mu);
+  g_pinned_big.push_back(b);
+}
 
 static cudaError_t pool_pinned(unsigned** out) {
   {
@@ -366,6 +398,9 @@ extern "C" int gcre_release_cached_memory(void) {
     cudaDeviceSynchronize();
     kv.second.release_all();
   }
+  std::lock_guard<std::mutex> lock2(g_pools.mu);
+  for (auto& b : g_pinned_big) cudaFreeHost(b.p);
+  g_pinned_big.clear();
   return GCRE_OK;
 }
 
@@ -793,16 +828,54 @@ extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint
   if (rows == 0) return GCRE_OK;
   ps->zero_pending = false;
   CK(cudaMemsetAsync(ps->d_rows, 0, (size_t)ps->size * row_words(ex) * 8, ex->stream));
-  CKS(upload_staged(ex, data, (size_t)cols * 4, rows, [&](const void* d_piece, size_t r0, size_t nr) {
-    const long long warps = (long long)nr * ex->W64;
-    pack_rows_i32_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>((const int32_t*)d_piece, (uint32_t)nr, cols,
-                                                                           ps->d_rows + r0 * row_words(ex), (int)row_words(ex), ex->W64);
-    CK(cudaGetLastError());
-    LAUNCHED();
-    return (int)GCRE_OK;
-  }));
+  // Where to pack.  The int matrix is 32x its bits: above a few tens of MB, and with enough host threads to stream it faster
+  // than the PCIe link would carry it (measured on the bench box, 600 MB matrix: 16 threads 112 GB/s, 8 threads 86 GB/s,
+  // link 52 GB/s), pack on the host and upload the bits; otherwise upload the ints and pack on the device.
+  // GCRE_HOST_PACK_THREADS sets the thread count (0 = never; default min(16, hardware threads)); one process per GPU on a
+  // shared host should divide the cores between the ranks (bench.py does).  GCRE_TEST_HOST_PACK=1 (test hook) forces the
+  // host path on small inputs.
+  int pack_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char* e = std::getenv("GCRE_HOST_PACK_THREADS")) pack_threads = std::atoi(e);
+  const char* force_host = std::getenv("GCRE_TEST_HOST_PACK");
+  const bool host_pack = (force_host && *force_host == '1' && pack_threads >= 1) ||
+                         (pack_threads >= 8 && (size_t)rows * cols * 4 >= ((size_t)32 << 20));
+  if (host_pack) {
+    const size_t w_in = ((size_t)cols + 63) / 64;  // words per row that carry data (<= W64)
+    PinnedBlock stage{nullptr, 0};
+    CK(pinned_big_acquire(std::max<size_t>((size_t)rows * w_in * 8, 8), &stage));
+    gcre_host::pack_i32_rows(data, rows, cols, static_cast<uint64_t*>(stage.p), w_in, pack_threads);
+    int rc = GCRE_OK;
+    if (w_in) {
+      rc = upload_staged(ex, stage.p, w_in * 8, rows, [&](const void* d_piece, size_t r0, size_t nr) {
+        place_rows_kernel<<<grid_for((long long)nr * (long long)w_in, 256), 256, 0, ex->stream>>>((const uint64_t*)d_piece, (uint32_t)nr, (int)w_in, (int)w_in,
+                                                                                               ps->d_rows + r0 * row_words(ex), (int)row_words(ex));
+        CK(cudaGetLastError());
+        LAUNCHED();
+        return (int)GCRE_OK;
+      });
+    }
+    pinned_big_release(stage);  // upload_staged has waited for its copies
+    CKS(rc);
+  } else {
+    CKS(upload_staged(ex, data, (size_t)cols * 4, rows, [&](const void* d_piece, size_t r0, size_t nr) {
+      const long long warps = (long long)nr * ex->W64;
+      pack_rows_i32_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>((const int32_t*)d_piece, (uint32_t)nr, cols,
+                                                                             ps->d_rows + r0 * row_words(ex), (int)row_words(ex), ex->W64);
+      CK(cudaGetLastError());
+      LAUNCHED();
+      return (int)GCRE_OK;
+    }));
+  }
   ps->max_half_pop = -1;
   drop_view(ps);
+  return GCRE_OK;
+}
+
+extern "C" int gcre_host_pack_i32(const int32_t* data, uint32_t rows, int cols, uint64_t* bits, int threads) {
+  if ((!data || !bits) && rows > 0 && cols > 0) return fail(GCRE_ERR_ARG, "null argument");
+  if (cols < 0) return fail(GCRE_ERR_ARG, "negative size");
+  if (threads <= 0) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (rows && cols) gcre_host::pack_i32_rows(data, rows, cols, bits, ((size_t)cols + 63) / 64, threads);
   return GCRE_OK;
 }
 

@@ -132,6 +132,10 @@ int gcre_pathset_size(const gcre_pathset* ps, uint32_t* size);
 int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint32_t rows, int cols);
 /* The same rows already packed: uint64[rows][words_per_row], patient c -> word c/64 bit c%64. */
 int gcre_pathset_load_bits(gcre_pathset* ps, const uint64_t* bits, uint32_t rows, int words_per_row);
+/* Host utility (no GPU involved): packs rows x cols int32 (non-zero = carrier, src/gcre_paths.h:65-67) into
+ * uint64[rows][ceil(cols/64)] for gcre_pathset_load_bits, on `threads` host threads (<= 0: all hardware threads, at most 16).
+ * gcre_pathset_load_i32 uses it by itself for large inputs when the host has >= 8 threads to spare. */
+int gcre_host_pack_i32(const int32_t* data, uint32_t rows, int cols, uint64_t* bits, int threads);
 
 /* PathSet::select(const vector<int>&)  (src/gcre_paths.h:82-92): new set, row k = row indices[k] of ps. */
 int gcre_pathset_select(const gcre_pathset* ps, const int32_t* indices, uint32_t n, gcre_pathset** out);

@@ -56,3 +56,23 @@ def test_product_does_not_import_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "gcre_oracle" in txt or "pyoracle" in txt:
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_host_pack_matches_numpy_packing():
+    """gcre_host_pack_i32 (host threads, no GPU): bit c of row r set iff data[r][c] != 0, LSB-first words (src/gcre_paths.h:65-67)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from geneticscre_b200 import _lib, synth
+
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    for rows, cols, threads in ((1, 1, 1), (3, 63, 2), (5, 64, 1), (7, 65, 3), (40, 200, 4), (33, 1000, 0), (2, 0, 1)):
+        data = (rng.random((rows, cols)) < 0.2).astype(np.int32) * rng.integers(-3, 4, size=(rows, cols), dtype=np.int32)
+        w = (cols + 63) // 64
+        out = np.full((rows, max(w, 1)), 0xAAAAAAAAAAAAAAAA, dtype=np.uint64)
+        _lib.check(lib.gcre_host_pack_i32(data.ctypes.data_as(C.POINTER(C.c_int32)), rows, cols, out.ctypes.data_as(C.POINTER(C.c_uint64)), threads))
+        if cols:
+            want = synth.pack_bits((data != 0).astype(np.int32))
+            assert np.array_equal(out[:, :w], want[:, :w]), (rows, cols)

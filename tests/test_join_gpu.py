@@ -112,9 +112,14 @@ def test_schedule_without_emitted_counts(engine, oracles, method, pc, monkeypatc
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
 
 
+@pytest.mark.parametrize("host_pack", ["0", "1"])
 @pytest.mark.parametrize("method", ["method1", "method2"])
-def test_int_matrix_inputs(engine, oracles, method):
-    """The R-facing formats: IntegerMatrix data (PathSet::load) and CaseORControl (setPermutedCases)."""
+def test_int_matrix_inputs(engine, oracles, method, host_pack, monkeypatch):
+    """The R-facing formats: IntegerMatrix data (PathSet::load) and CaseORControl (setPermutedCases).  Large matrices are
+    packed to bits by host threads before the upload, small ones on the device; GCRE_TEST_HOST_PACK=1 forces the host path
+    (3 threads) on this small input."""
+    monkeypatch.setenv("GCRE_TEST_HOST_PACK", host_pack)
+    monkeypatch.setenv("GCRE_HOST_PACK_THREADS", "3")
     w = synth.make_workload(90, 110, 100, 300, 50, seed=77, max_path_length=4, real_table=True, max_freq=0.1, zero_frac=0.2)
     want, kw, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, 6, use_int_matrices=True, int_perms=True)
     got, kg, _ = helpers.run_schedule(engine.JoinExec, engine.UidRelSet, w, method, 4, 6, use_int_matrices=True, int_perms=True)
