@@ -502,7 +502,6 @@ def main():
         is_case[: w.n_cases] = True
         perm_i = torch.from_numpy((bits == is_case[None, :]).astype(np.int32)).pin_memory().numpy()
         table = torch.from_numpy(np.ascontiguousarray(w.value_table)).pin_memory().numpy()
-        h2d = (data1_i.nbytes + data2_i.nbytes + perm_i.nbytes + table.nbytes) * 2  # per method
         d2h_holder = [0]
 
         uid_host = {k: api.UidRelSet(lv[k].path_length, lv[k].src, lv[k].trg, lv[k].count, lv[k].location, lv[k].signs) for k in names}
@@ -513,11 +512,45 @@ def main():
 
         for u in uid_host.values():
             u._packed, u.signs = pinned(u._packed), pinned(u.signs)
-        h2d += 2 * sum(u._packed.nbytes + u.signs.nbytes for u in uid_host.values())
+        idx_bytes = sum(u._packed.nbytes + u.signs.nbytes for u in uid_host.values())
+        W1 = (n + 63) // 64
+        bits_bytes = (data1_i.shape[0] + data2_i.shape[0]) * W1 * 8
+        pack_threads = int(os.environ["GCRE_HOST_PACK_THREADS"])
+        host_packed = pack_threads >= 8 and min(data1_i.nbytes, data2_i.nbytes) >= (32 << 20)  # gcre_pathset_load_i32's own rule
+        # Multi-GPU, permutation blocks: cohort matrices and value table are the same on every rank, so rank 0 alone reads them
+        # (host-packed), uploads them once per step and NCCL broadcasts the 47 MB of bits + the table over NVLink; every rank
+        # uploads only its own block of permutations.  Without this eight ranks pull 8 x 2.9 GB per step through one host.
+        fanout = world > 1 and shard_perms
+        if fanout:
+            h2d = (bits_bytes + table.nbytes if rank == 0 else 0) + 2 * (perm_i.nbytes + idx_bytes)
+            bits1_h = torch.zeros((data1_i.shape[0], W1), dtype=torch.int64).pin_memory()
+            bits2_h = torch.zeros((data2_i.shape[0], W1), dtype=torch.int64).pin_memory()
+            table_h = torch.from_numpy(table)
+        else:
+            h2d = 2 * ((bits_bytes if host_packed else data1_i.nbytes + data2_i.nbytes) + perm_i.nbytes + table.nbytes + idx_bytes)  # per method
+        host_input_bytes = 2 * (data1_i.nbytes + data2_i.nbytes + perm_i.nbytes + table.nbytes + idx_bytes)
         # The two methods are independent jobs (two GWASPA() calls upstream).  Run from two host threads on two streams the
         # second method's uploads hide under the first method's joins; the collectives stay on the main thread, in order.
         overlap = a.e2e_threads > 1 and (world == 1 or shard_perms)
         e2e_streams = {m: (torch.cuda.Stream() if overlap else stream) for m in ("method1", "method2")}
+        shared = {}
+
+        def fan_out():
+            """rank 0: pack + upload once; everyone: receive over NVLink (main thread, default process group)."""
+            with torch.cuda.stream(stream):
+                tab_d = torch.empty(table.shape, dtype=torch.float64, device="cuda")
+                b1_d = torch.empty(bits1_h.shape, dtype=torch.int64, device="cuda")
+                b2_d = torch.empty(bits2_h.shape, dtype=torch.int64, device="cuda")
+                if rank == 0:
+                    tab_d.copy_(table_h, non_blocking=True)
+                    api.host_pack(data1_i, threads=min(16, os.cpu_count() or 1), out=bits1_h.numpy().view(np.uint64))
+                    b1_d.copy_(bits1_h, non_blocking=True)
+                    api.host_pack(data2_i, threads=min(16, os.cpu_count() or 1), out=bits2_h.numpy().view(np.uint64))
+                    b2_d.copy_(bits2_h, non_blocking=True)
+                for t in (tab_d, b1_d, b2_d):
+                    dist.broadcast(t, src=0)
+            stream.synchronize()  # the method threads launch on their own streams
+            shared.update(table=tab_d, bits1=b1_d, bits2=b2_d)
 
         def e2e_method(method, results, gate_in, gate_out):
             t_in = time.perf_counter()
@@ -530,10 +563,16 @@ def main():
                 ex.set_stream(e2e_streams[method].cuda_stream)
                 ex.kernel = kernel
                 ex.top_k = a.top_k
-                ex.setValueTable(table)
-                ex.setPermutedCases(perm_i)
-                d1 = ex.createPathSet(data1_i.shape[0]); d1.load(data1_i)
-                d2 = ex.createPathSet(data2_i.shape[0]); d2.load(data2_i)
+                if fanout:
+                    ex.setValueTableDevice(shared["table"].data_ptr(), table.shape[0], table.shape[1])
+                    ex.setPermutedCases(perm_i)
+                    d1 = ex.createPathSet(data1_i.shape[0]); d1.load_bits_device(shared["bits1"].data_ptr(), data1_i.shape[0], W1)
+                    d2 = ex.createPathSet(data2_i.shape[0]); d2.load_bits_device(shared["bits2"].data_ptr(), data2_i.shape[0], W1)
+                else:
+                    ex.setValueTable(table)
+                    ex.setPermutedCases(perm_i)
+                    d1 = ex.createPathSet(data1_i.shape[0]); d1.load(data1_i)
+                    d2 = ex.createPathSet(data2_i.shape[0]); d2.load(data2_i)
             finally:
                 if gate_out is not None:
                     gate_out.set()
@@ -551,6 +590,11 @@ def main():
 
             d2h = 0
             results = {}
+            if fanout:
+                t_f = time.perf_counter()
+                fan_out()
+                if dbg:
+                    sys.stderr.write(f"[bench] rank {rank} e2e fan-out: {(time.perf_counter() - t_f) * 1e3:.1f} ms\n")
             if overlap:
                 gate = threading.Event()
                 errs = []
@@ -586,6 +630,9 @@ def main():
 
         step_e2e()
         sync_all()
+        gc.collect()
+        gc.freeze()
+        gc.disable()  # as in the resident region: a cyclic GC pass costs 100+ ms with torch imported
         t0 = time.perf_counter()
         e2e_steps = max(1, min(a.steps, 3))
         for i in range(e2e_steps):
@@ -595,10 +642,15 @@ def main():
                 sys.stderr.write(f"[bench] rank {rank} e2e step {i}: {(time.perf_counter() - t_dbg) * 1e3:.1f} ms\n")
         sync_all()
         dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+        gc.enable()
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": pp_step / float(dt.item()), "unit": "pair*perm/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_holder[0]),
-               "ms_per_step": float(dt.item()) * 1e3, "steps": e2e_steps,
+               "ms_per_step": float(dt.item()) * 1e3, "steps": e2e_steps, "host_input_bytes_per_step": int(host_input_bytes),
+               "input_path": ("rank 0 packs the int matrices on host threads and uploads bits + table once per step, NCCL broadcast to the other ranks; "
+                              "every rank uploads its own permutation block" if fanout else
+                              "int matrices packed to bits by host threads inside gcre_pathset_load_i32, bits uploaded" if host_packed else
+                              "int matrices uploaded, packed on the device"),
                "host_threads": 2 if overlap else 1,
                "note": "host IntegerMatrix data + CaseORControl int matrix + f64 value table + join indices uploaded every step (pinned), per method; "
                        "the two methods are submitted from two host threads on two streams, so one method's uploads overlap the other's joins"

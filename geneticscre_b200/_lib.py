@@ -55,6 +55,8 @@ SYMBOLS = {
     "gcre_pathset_size": (_I, [_VP, C.POINTER(_U32)]),
     "gcre_pathset_load_i32": (_I, [_VP, C.POINTER(C.c_int32), _U32, _I]),
     "gcre_pathset_load_bits": (_I, [_VP, C.POINTER(C.c_uint64), _U32, _I]),
+    "gcre_pathset_load_bits_device": (_I, [_VP, _VP, _U32, _I]),
+    "gcre_exec_set_value_table_device": (_I, [_VP, _VP, _I, _I]),
     "gcre_host_pack_i32": (_I, [C.POINTER(C.c_int32), _U32, _I, C.POINTER(C.c_uint64), _I]),
     "gcre_pathset_select": (_I, [_VP, C.POINTER(C.c_int32), _U32, C.POINTER(_VP)]),
     "gcre_pathset_set_row": (_I, [_VP, _U32, C.POINTER(C.c_uint64)]),

@@ -117,6 +117,10 @@ class PathSet:
         b = _as(bits, np.uint64)
         check(self.ex._lib.gcre_pathset_load_bits(self._h, _ptr(b, C.c_uint64), b.shape[0], b.shape[1] if b.ndim == 2 else 0))
 
+    def load_bits_device(self, device_ptr, rows, words_per_row):
+        """Packed rows already in this GPU's memory (e.g. after an NCCL broadcast); ordered on the exec's stream."""
+        check(self.ex._lib.gcre_pathset_load_bits_device(self._h, C.c_void_p(int(device_ptr)), int(rows), int(words_per_row)))
+
     def select(self, indices):
         """PathSet::select (src/gcre_paths.h:82-92)."""
         i = _as(indices, np.int32)
@@ -187,6 +191,10 @@ class JoinExec:
             t = t.reshape(0, 0)
         check(self._lib.gcre_exec_set_value_table(self._h, _ptr(t, C.c_double), t.shape[0], t.shape[1]))
 
+    def setValueTableDevice(self, device_ptr, rows, cols):
+        """The value table from a buffer in this GPU's memory (multi-GPU fan-out); ordered on the exec's stream."""
+        check(self._lib.gcre_exec_set_value_table_device(self._h, C.c_void_p(int(device_ptr)), int(rows), int(cols)))
+
     def generateValueTable(self):
         """getValuesTable (R/Utils.R:137-159) on the device for this exec's (num_cases, num_ctrls) (extension)."""
         check(self._lib.gcre_exec_generate_value_table(self._h))
@@ -249,6 +257,17 @@ class JoinExec:
         out = np.zeros(max(self.iters_requested, 1), dtype=np.float64)
         check(self._lib.gcre_exec_read_perm_max(self._h, _ptr(out, C.c_double)))
         return out[: self.iters_requested].copy()
+
+
+def host_pack(data, threads=0, out=None):
+    """int matrix (any non-zero = carrier) -> uint64[rows][ceil(cols/64)] on host threads (gcre_host_pack_i32)."""
+    d = _as(data, np.int32)
+    rows, cols = d.shape
+    w = (cols + 63) // 64
+    if out is None:
+        out = np.zeros((rows, w), dtype=np.uint64)
+    check(_lib.load().gcre_host_pack_i32(_ptr(d, C.c_int32), rows, cols, _ptr(out, C.c_uint64), int(threads)))
+    return out
 
 
 def merge_topk(score_lists, top_k):

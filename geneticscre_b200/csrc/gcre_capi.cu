@@ -871,6 +871,44 @@ extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint
   return GCRE_OK;
 }
 
+// Device-side inputs (multi-GPU fan-out: one rank uploads, NCCL broadcasts over NVLink, every rank adopts the buffer).
+// Ordered on the exec's stream; the caller's buffer must stay valid until that stream has passed the copy (any later join
+// of this exec synchronises it).
+extern "C" int gcre_pathset_load_bits_device(gcre_pathset* ps, const uint64_t* d_bits, uint32_t rows, int words_per_row) {
+  if (!ps || (!d_bits && rows > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
+  CKS(use_device(ex));
+  if (rows != ps->size) return fail(GCRE_ERR_ASSERT, "assertion");
+  if (rows > 0 && (words_per_row < 0 || words_per_row > ex->W64)) return fail(GCRE_ERR_RANGE, "assertion");
+  if (rows == 0) return GCRE_OK;
+  ps->zero_pending = false;
+  CK(cudaMemsetAsync(ps->d_rows, 0, (size_t)ps->size * row_words(ex) * 8, ex->stream));
+  if (words_per_row > 0) {
+    place_rows_kernel<<<grid_for((long long)rows * words_per_row, 256), 256, 0, ex->stream>>>(d_bits, rows, words_per_row, words_per_row, ps->d_rows,
+                                                                                             (int)row_words(ex));
+    CK(cudaGetLastError());
+    LAUNCHED();
+  }
+  ps->max_half_pop = -1;
+  drop_view(ps);
+  return GCRE_OK;
+}
+
+extern "C" int gcre_exec_set_value_table_device(gcre_exec* ex, const double* d_table, int rows, int cols) {
+  if (!ex || (!d_table && rows > 0 && cols > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  if (rows < 0 || cols < 0) return fail(GCRE_ERR_ARG, "negative table size");
+  CKS(use_device(ex));
+  dev_free(ex, ex->d_vt);
+  ex->d_vt = nullptr;
+  ex->vt_rows = rows;
+  ex->vt_cols = cols;
+  const size_t bytes = std::max<size_t>((size_t)rows * cols, 1) * 8;
+  CK(dev_alloc(ex, (void**)&ex->d_vt, bytes));
+  if ((size_t)rows * cols) CK(cudaMemcpyAsync(ex->d_vt, d_table, (size_t)rows * cols * 8, cudaMemcpyDeviceToDevice, ex->stream));
+  ex->diag_cap = -1;
+  return GCRE_OK;
+}
+
 extern "C" int gcre_host_pack_i32(const int32_t* data, uint32_t rows, int cols, uint64_t* bits, int threads) {
   if ((!data || !bits) && rows > 0 && cols > 0) return fail(GCRE_ERR_ARG, "null argument");
   if (cols < 0) return fail(GCRE_ERR_ARG, "negative size");

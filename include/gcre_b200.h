@@ -105,6 +105,8 @@ int gcre_exec_set_stream(gcre_exec* ex, void* cuda_stream);
 /* JoinExec::setValueTable(const vec2d_d&)  (src/join_base.cpp:62-80).  Row-major rows x cols doubles, [cases][ctrls].
  * Entries outside the supplied table read as -1.0, as in the reference's (n+1)x(n+1) padding. */
 int gcre_exec_set_value_table(gcre_exec* ex, const double* table, int rows, int cols);
+/* The same from a buffer in this exec's device memory (see gcre_pathset_load_bits_device for the ordering rule). */
+int gcre_exec_set_value_table_device(gcre_exec* ex, const double* d_table, int rows, int cols);
 
 /* getValuesTable(nCases, nControls) (R/Utils.R:137-159) computed on the device for this exec's own case/control counts:
  * vt[x][y] = -log(two-sided hypergeometric p of x cases among x + y carriers), infinities -> max finite + 1.  The R version
@@ -132,6 +134,9 @@ int gcre_pathset_size(const gcre_pathset* ps, uint32_t* size);
 int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint32_t rows, int cols);
 /* The same rows already packed: uint64[rows][words_per_row], patient c -> word c/64 bit c%64. */
 int gcre_pathset_load_bits(gcre_pathset* ps, const uint64_t* bits, uint32_t rows, int words_per_row);
+/* The same from a buffer in this exec's device memory (e.g. the target of an NCCL broadcast): ordered on the exec's stream,
+ * no host synchronisation; d_bits must stay valid until that stream has passed the copy (any later join synchronises). */
+int gcre_pathset_load_bits_device(gcre_pathset* ps, const uint64_t* d_bits, uint32_t rows, int words_per_row);
 /* Host utility (no GPU involved): packs rows x cols int32 (non-zero = carrier, src/gcre_paths.h:65-67) into
  * uint64[rows][ceil(cols/64)] for gcre_pathset_load_bits, on `threads` host threads (<= 0: all hardware threads, at most 16).
  * gcre_pathset_load_i32 uses it by itself for large inputs when the host has >= 8 threads to spare. */

@@ -170,6 +170,40 @@ def test_two_execs_on_two_host_threads(engine, oracles):
             helpers.assert_same_results(got[m][lvl], want[m][lvl], what=f"{m} L{lvl} (threaded)")
 
 
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_device_side_inputs(engine, oracles, method, monkeypatch):
+    """gcre_pathset_load_bits_device / gcre_exec_set_value_table_device (inputs that already sit in GPU memory, e.g. after
+    an NCCL broadcast in a multi-GPU job) give the same results as the host-buffer calls."""
+    import torch
+
+    keep = []
+
+    def to_device(arr, view):
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(view)).cuda()
+        torch.cuda.synchronize()  # the exec launches on its own stream
+        keep.append(t)
+        return t
+
+    def load_bits_via_device(self, bits):
+        t = to_device(bits, np.int64)
+        self.load_bits_device(t.data_ptr(), bits.shape[0], bits.shape[1])
+
+    def table_via_device(self, table):
+        t = to_device(table, np.float64)
+        self.setValueTableDevice(t.data_ptr(), table.shape[0], table.shape[1])
+
+    w = synth.make_workload(120, 131, 90, 320, 70, seed=88, max_path_length=4, real_table=True, max_freq=0.1, zero_frac=0.2)
+    want, kw, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, 6)
+    monkeypatch.setattr(engine.PathSet, "load_bits", load_bits_via_device)
+    monkeypatch.setattr(engine.JoinExec, "setValueTable", table_via_device)
+    got, kg, _ = helpers.run_schedule(engine.JoinExec, engine.UidRelSet, w, method, 4, 6)
+    assert len(keep) >= 3
+    for k in kw:
+        assert np.array_equal(kg[k], kw[k])
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
+
+
 @pytest.mark.parametrize("rows", [3, 20])
 def test_perm_rows_reused_or_truncated(engine, oracles, rows):
     """Fewer perm rows than iterations are reused cyclically, surplus rows ignored (src/join_base.cpp:89-90,116-123)."""
