@@ -837,12 +837,15 @@ extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint
   int pack_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
   if (const char* e = std::getenv("GCRE_HOST_PACK_THREADS")) pack_threads = std::atoi(e);
   const char* force_host = std::getenv("GCRE_TEST_HOST_PACK");
-  const bool host_pack = (force_host && *force_host == '1' && pack_threads >= 1) ||
+  bool host_pack = (force_host && *force_host == '1' && pack_threads >= 1) ||
                          (pack_threads >= 8 && (size_t)rows * cols * 4 >= ((size_t)32 << 20));
+  const size_t w_in = ((size_t)cols + 63) / 64;  // words per row that carry data (<= W64)
+  PinnedBlock stage{nullptr, 0};
+  if (host_pack && pinned_big_acquire(std::max<size_t>((size_t)rows * w_in * 8, 8), &stage) != cudaSuccess) {
+    cudaGetLastError();  // no page-locked memory to be had: pack on the device instead
+    host_pack = false;
+  }
   if (host_pack) {
-    const size_t w_in = ((size_t)cols + 63) / 64;  // words per row that carry data (<= W64)
-    PinnedBlock stage{nullptr, 0};
-    CK(pinned_big_acquire(std::max<size_t>((size_t)rows * w_in * 8, 8), &stage));
     gcre_host::pack_i32_rows(data, rows, cols, static_cast<uint64_t*>(stage.p), w_in, pack_threads);
     int rc = GCRE_OK;
     if (w_in) {

@@ -70,9 +70,15 @@ void pack_i32_rows(const int32_t* data, size_t rows, int cols, uint64_t* out, si
     return;
   }
   std::vector<std::thread> pool;
-  pool.reserve(threads);
-  for (int t = 0; t < threads; t++) pool.emplace_back(work, rows * t / threads, rows * (t + 1) / threads);
+  bool all_started = true;
+  try {
+    pool.reserve(threads);
+    for (int t = 0; t < threads; t++) pool.emplace_back(work, rows * t / threads, rows * (t + 1) / threads);
+  } catch (...) {  // thread creation refused (resource limits): finish on the calling thread - the work is idempotent
+    all_started = false;
+  }
   for (auto& th : pool) th.join();
+  if (!all_started) work(0, rows);
 }
 
 }  // namespace gcre_host

@@ -258,14 +258,16 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
   using namespace sparse;
   const CT* car0 = static_cast<const CT*>(s.car0);
   const CT* car1 = static_cast<const CT*>(s.car1);
-  __shared__ uint32_t s_base[WARPS][M][16][32];          // base counts per warp / half / packed register / lane
+  // per-thread slots indexed [half][register][threadIdx.x]: the address is a constant plus 4 * threadIdx.x, which costs two
+  // instructions to rematerialise under register pressure (indexed [warp][..][lane] it cost ten, 5 % of method 2's issue slots)
+  __shared__ uint32_t s_base[M][16][THREADS];              // base counts per half / packed register / thread
   __shared__ __align__(16) uint32_t s_queue[WARPS][QCAP];  // row offsets (carrier * Iw) of the partner's carriers that survive the filter
   // method 2: the two halves go through ONE instance of the filter / accumulate / flush code (a rolled loop), their counts
   // parked here for the look-up stage: unrolled per half the kernel was 62 KB of SASS and lost more issue slots to
   // instruction fetch than to memory latency (profiles/r1_sparse_final_full.txt, no_instruction 4.1 vs long_scoreboard 4.0)
-  __shared__ uint32_t s_cnt[WARPS][M == 2 ? 2 : 1][M == 2 ? 16 : 1][32];
+  __shared__ uint32_t s_cnt[M == 2 ? 2 : 1][M == 2 ? 16 : 1][THREADS];
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Wp = a.Wp, Iw = a.Iw;  // Iw: words per patient row of pt (a multiple of 32: every lane owns a valid word)
   const int row_words = Wp * M;
   const unsigned long long n_work = s.n_units * (unsigned long long)s.n_perm_blocks;
@@ -376,10 +378,10 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const uint4 v = __ldcs(B + q * 32);  // read once per unit: keep it from displacing the mask rows in L1
-          s_base[warp][h][4 * q][lane] = v.x;
-          s_base[warp][h][4 * q + 1][lane] = v.y;
-          s_base[warp][h][4 * q + 2][lane] = v.z;
-          s_base[warp][h][4 * q + 3][lane] = v.w;
+          s_base[h][4 * q][tid] = v.x;
+          s_base[h][4 * q + 1][tid] = v.y;
+          s_base[h][4 * q + 2][tid] = v.z;
+          s_base[h][4 * q + 3][tid] = v.w;
         }
       } else {
         uint32_t acc[16];
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 #pragma unroll 1
         for (uint32_t i = 0; i < plen; i += 8) add8(acc, car0 + o + i, i + 8 >= plen);
 #pragma unroll
-        for (int i = 0; i < 16; i++) s_base[warp][h][i][lane] = acc[i];
+        for (int i = 0; i < 16; i++) s_base[h][i][tid] = acc[i];
       }
     }
     __syncwarp();
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 #pragma unroll 1
       for (int h = 0; h < M; h++) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) c16[i] = PC ? 0u : s_base[warp][h][i][lane];
+        for (int i = 0; i < 16; i++) c16[i] = PC ? 0u : s_base[h][i][tid];
         // joined half h = upstream half h | partner half hh   (src/methods.h:137-145)
         const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
         const size_t item = (size_t)loc * M + hh;
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
         }
         if (M == 2) {
 #pragma unroll
-          for (int i = 0; i < 16; i++) s_cnt[warp][h][i][lane] = c16[i];
+          for (int i = 0; i < 16; i++) s_cnt[h][i][tid] = c16[i];
           if (h == 0) { nd[0] = ndh; ncn[0] = ncnh; pitem[0] = item; } else { nd[M - 1] = ndh; ncn[M - 1] = ncnh; pitem[M - 1] = item; }
         } else {
           nd[0] = ndh;
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const int i = 4 * q + k;
-                const uint32_t v = s_base[warp][0][i][lane] + pr[k] - c16[i];
+                const uint32_t v = s_base[0][i][tid] + pr[k] - c16[i];
                 best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __ldg(row + (v & 0xffffu)));
                 best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __ldg(row + (v >> 16)));
               }
@@ -502,8 +504,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const int i = 4 * q + k;
-                const uint32_t vp = s_base[warp][0][i][lane] + prp[k] - s_cnt[warp][0][M == 2 ? i : 0][lane];
-                const uint32_t vn = s_base[warp][M - 1][i][lane] + prn[k] - s_cnt[warp][M == 2 ? 1 : 0][M == 2 ? i : 0][lane];
+                const uint32_t vp = s_base[0][i][tid] + prp[k] - s_cnt[0][M == 2 ? i : 0][tid];
+                const uint32_t vn = s_base[M - 1][i][tid] + prn[k] - s_cnt[M == 2 ? 1 : 0][M == 2 ? i : 0][tid];
                 // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
                 const double vlo = __ldg(rowp + (vp & 0xffffu)) + __ldg(rown - (vn & 0xffffu));
                 const double vhi = __ldg(rowp + (vp >> 16)) + __ldg(rown - (vn >> 16));
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           const double* rown = a.diagDM + diag_base(tn) + tn;
 #pragma unroll
           for (int b = 0; b < 32; b++) {
-            const uint32_t vp = s_cnt[warp][0][M == 2 ? GCRE_C16_REG(b) : 0][lane], vn = s_cnt[warp][M == 2 ? 1 : 0][M == 2 ? GCRE_C16_REG(b) : 0][lane];
+            const uint32_t vp = s_cnt[0][M == 2 ? GCRE_C16_REG(b) : 0][tid], vn = s_cnt[M == 2 ? 1 : 0][M == 2 ? GCRE_C16_REG(b) : 0][tid];
             const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
             const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
             // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
@@ -546,8 +548,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             if (M == 1) __stcs(out + q * 32, make_uint4(c16[4 * q], c16[4 * q + 1], c16[4 * q + 2], c16[4 * q + 3]));
-            else __stcs(out + q * 32, make_uint4(s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q : 0][lane], s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 1 : 0][lane],
-                                          s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 2 : 0][lane], s_cnt[warp][M == 2 ? h : 0][M == 2 ? 4 * q + 3 : 0][lane]));
+            else __stcs(out + q * 32, make_uint4(s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q : 0][tid], s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 1 : 0][tid],
+                                          s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 2 : 0][tid], s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 3 : 0][tid]));
           }
           if (first_pb && lane == 0) {
             s.len_res[r * M + h] = t0[h == 0 ? 0 : M - 1] + nd[h == 0 ? 0 : M - 1];
