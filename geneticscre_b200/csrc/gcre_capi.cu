@@ -1431,7 +1431,33 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     const char* emit_env = std::getenv("GCRE_TEST_EMIT");
     const bool emit = keep && pair_lo == 0 && pair_hi == total && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
                       (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
-    if (!emit && precount_preferred(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget)) {
+    int pc_mode = emit ? PRECOUNT_NO : precount_mode(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget);
+    if (pc_mode == PRECOUNT_SAMPLE) {
+      // how much of a partner row is already in its upstream row: 2,048 pairs spread over the join (~40 us incl. the read-back)
+      JoinParams q;
+      memset(&q, 0, sizeof q);
+      q.p0 = paths0->d_rows;
+      q.p1 = paths1->d_rows;
+      q.Wp = ex->Wp;
+      q.prefix = (const unsigned long long*)us->prefix.p;
+      q.location = (const uint32_t*)us->loc.p;
+      q.n_uids = n_uids;
+      q.signs = (const int32_t*)us->signs.p;
+      q.path_length = path_length;
+      const int n_samples = 2048;
+      unsigned long long* d_sums = reinterpret_cast<unsigned long long*>(ex->d_scalars + 8);
+      CK(cudaMemsetAsync(d_sums, 0, 2 * sizeof(unsigned long long), ex->stream));
+      if (ex->M == 1) sample_overlap_kernel<1><<<grid_for((long long)n_samples * 32, 256), 256, 0, ex->stream>>>(q, pair_lo, pair_hi, n_samples, d_sums);
+      else sample_overlap_kernel<2><<<grid_for((long long)n_samples * 32, 256), 256, 0, ex->stream>>>(q, pair_lo, pair_hi, n_samples, d_sums);
+      CK(cudaGetLastError());
+      LAUNCHED();
+      CK(cudaMemcpyAsync(ex->h_scalars + 8, d_sums, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ex->stream));
+      CK(cudaStreamSynchronize(ex->stream));
+      unsigned long long sums[2];
+      memcpy(sums, ex->h_scalars + 8, sizeof sums);
+      pc_mode = (sums[0] * 10 < sums[1] * 6) ? PRECOUNT_YES : PRECOUNT_NO;
+    }
+    if (pc_mode == PRECOUNT_YES) {
       CKS(ensure_precount(ex, const_cast<gcre_pathset*>(paths1)));
       sp.pcnt1 = paths1->view.pcnt;
     }

@@ -674,16 +674,52 @@ static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinPara
 
 // Pre-counted partners replace the walk over the partner's new carriers by a 2 KB read plus a walk over the carriers
 // the two rows SHARE.  In the level schedule of the reference a partner path always starts at the gene the upstream path
-// ends in, so the shared part is about as long as the new part and the form loses (BASELINE config 3, ms per launch,
-// delta / pre-counted: level 4 method 1 13.1 / 15.0, method 2 22.4 / 27.0; level 5 147 / 123 and 244 / 242; level 3, where
-// the partners are single genes, 2.7 / 2.4 and 5.8 / 5.8).  It is therefore opt-in: GCRE_PRECOUNT=1 (GCRE_TEST_PRECOUNT
-// in the tests) selects it for joins whose table fits the budget.
-static inline bool precount_preferred(unsigned long long pairs, unsigned long long partner_rows, int M, int n_perm_blocks, size_t budget_bytes) {
-  if (partner_rows == 0 || pairs == 0) return false;
-  if ((size_t)partner_rows * M * n_perm_blocks * 2048 > budget_bytes) return false;
+// ends in, so at level 4 the shared part is as long as the new part and the form loses (BASELINE config 3, ms per launch,
+// delta / pre-counted: level 4 method 1 13.1 / 15.0, method 2 22.4 / 27.0), while at level 5 (two new genes per shared one)
+// and level 3 (single-gene partners, nothing shared) method 1 gains: 147 / 123 and 2.7 / 2.4; method 2, whose look-ups
+// dominate, does not (244 / 242, 5.8 / 5.8).  So: method 1, large score-only joins, and only when a sample of the pairs
+// (sample_overlap_kernel) shows the shared part below 0.6 of the new part.  GCRE_PRECOUNT=1 / 0 (GCRE_TEST_PRECOUNT in the
+// tests) forces it on / off.
+enum { PRECOUNT_NO = 0, PRECOUNT_YES = 1, PRECOUNT_SAMPLE = 2 };
+static inline int precount_mode(unsigned long long pairs, unsigned long long partner_rows, int M, int n_perm_blocks, size_t budget_bytes) {
+  if (partner_rows == 0 || pairs == 0) return PRECOUNT_NO;
+  if ((size_t)partner_rows * M * n_perm_blocks * 2048 > budget_bytes) return PRECOUNT_NO;
   const char* f = std::getenv("GCRE_TEST_PRECOUNT");
   if (!f) f = std::getenv("GCRE_PRECOUNT");
-  return f && *f == '1';
+  if (f && (*f == '0' || *f == '1')) return *f == '1' ? PRECOUNT_YES : PRECOUNT_NO;
+  if (f && *f == 's') return PRECOUNT_SAMPLE;  // test hook: let the sample decide whatever the method and the size
+  return (M == 1 && pairs >= (1ull << 20)) ? PRECOUNT_SAMPLE : PRECOUNT_NO;
+}
+
+// One warp per sampled pair (evenly spaced over the pairs of the join): out[0] += |partner & upstream|,
+// out[1] += |partner & ~upstream| over the halves that are joined (method 2: routed by need_flip).
+template <int M>
+__global__ void sample_overlap_kernel(const JoinParams a, unsigned long long pair_lo, unsigned long long pair_hi, int n_samples,
+                                      unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (w >= n_samples) return;
+  const unsigned long long p = pair_lo + (pair_hi - pair_lo) * (unsigned long long)w / (unsigned long long)n_samples;
+  const uint32_t idx = find_uid(a.prefix, a.n_uids, p);
+  const uint32_t loc = a.location[idx] + (uint32_t)(p - a.prefix[idx]);
+  const bool flip = (M == 2) ? need_flip(a.path_length, a.signs, idx, loc) : true;
+  const uint64_t* u = a.p0 + (size_t)idx * a.Wp * M;
+  const uint64_t* v = a.p1 + (size_t)loc * a.Wp * M;
+  unsigned ov = 0, dl = 0;
+  for (int h = 0; h < M; h++) {
+    const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
+    for (int k = lane; k < a.Wp; k += 32) {
+      const uint64_t x = u[h * a.Wp + k], y = v[hh * a.Wp + k];
+      ov += __popcll(x & y);
+      dl += __popcll(y & ~x);
+    }
+  }
+  ov = __reduce_add_sync(0xffffffffu, ov);
+  dl = __reduce_add_sync(0xffffffffu, dl);
+  if (lane == 0) {
+    atomicAdd(out, (unsigned long long)ov);
+    atomicAdd(out + 1, (unsigned long long)dl);
+  }
 }
 
 }  // namespace gcre

@@ -171,6 +171,23 @@ def test_two_execs_on_two_host_threads(engine, oracles):
 
 
 @pytest.mark.parametrize("method", ["method1", "method2"])
+def test_precount_chosen_by_sampled_overlap(engine, oracles, method, monkeypatch):
+    """Large method-1 score-only joins sample the overlap between partner and upstream rows to pick the kernel form;
+    GCRE_TEST_PRECOUNT=sample applies that rule to every score-only join here.  Level 1b (empty upstream rows: nothing shared)
+    must come out pre-counted, level 4 of this schedule (partner shares a gene with the upstream path) must not."""
+    monkeypatch.setenv("GCRE_TEST_PRECOUNT", "sample")
+    w = synth.make_workload(257, 300, 200, 800, 257, seed=4243, max_path_length=5, real_table=True, max_freq=0.12, zero_frac=0.3)
+    want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 5, 8)
+    got, kept, _ = run_engine(engine, w, method, 5, 8, _lib.KERNEL_SPARSE)
+    for k in kept_want:
+        assert np.array_equal(kept[k], kept_want[k]), f"kept {k} differs"
+    for lvl in want:
+        helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
+    assert got["1b"].info["precounted"] is True
+    assert got["4"].info["precounted"] is False
+
+
+@pytest.mark.parametrize("method", ["method1", "method2"])
 def test_device_side_inputs(engine, oracles, method, monkeypatch):
     """gcre_pathset_load_bits_device / gcre_exec_set_value_table_device (inputs that already sit in GPU memory, e.g. after
     an NCCL broadcast in a multi-GPU job) give the same results as the host-buffer calls."""
