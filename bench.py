@@ -605,8 +605,10 @@ def main():
                     except BaseException as e:  # re-raised on the main thread
                         errs.append(e)
 
-                th = [threading.Thread(target=guarded, args=("method2", results, None, gate)),
-                      threading.Thread(target=guarded, args=("method1", results, gate, None))]
+                # method 1 first: its shorter joins are done by the time method 2's uploads finish (65.9 vs 68.2 ms the other way round)
+                first, second = ("method2", "method1") if os.environ.get("GCRE_BENCH_E2E_ORDER") == "21" else ("method1", "method2")
+                th = [threading.Thread(target=guarded, args=(first, results, None, gate)),
+                      threading.Thread(target=guarded, args=(second, results, gate, None))]
                 for t in th:
                     t.start()
                 for t in th:
