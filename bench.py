@@ -487,7 +487,7 @@ def main():
             for k in names:
                 inf = last_out[method][0][k]
                 kms = float(inf["kernel_ms"])
-                per_level[method][k] = {"pairs": int(inf["pairs"]), "kernel_ms": kms, "kernel": {1: "dense", 2: "sparse"}.get(inf["kernel"], "none") + ("+precount" if inf.get("precounted") else ""),
+                per_level[method][k] = {"pairs": int(inf["pairs"]), "kernel_ms": kms, "kernel": {1: "dense", 2: "sparse"}.get(inf["kernel"], "none") + ("+precount" if inf.get("precounted") else "") + ("+split-carrier" if inf.get("split_carrier") else ""),
                                         "pair_perm_per_s": (inf["pairs"] * w.n_perms / (kms * 1e-3)) if kms > 0 else None}
 
     # ---- end-to-end through the reference-facing calls with HOST buffers (R-facing int matrices), N GPUs ----

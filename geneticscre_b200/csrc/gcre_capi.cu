@@ -23,6 +23,7 @@
 #include "setup_kernels.cuh"
 #include "join_dense.cuh"
 #include "join_sparse.cuh"
+#include "join_sparse_sc.cuh"
 #include "value_table.cuh"
 
 using namespace gcre;
@@ -1429,9 +1430,12 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     if (const char* mb = std::getenv("GCRE_PRECOUNT_MAX_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
     // kept rows take their counts along (join_sparse.cuh) when the join writes all of them; GCRE_TEST_EMIT=0 (test hook) turns it off
     const char* emit_env = std::getenv("GCRE_TEST_EMIT");
-    const bool emit = keep && pair_lo == 0 && pair_hi == total && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
+    // <= 128 permutations: the split-carrier kernel (join_sparse_sc.cuh) runs instead and neither writes nor reads count tables
+    const bool few_perms = ex->Ip <= sparse_sc::MAX_PERMS && sp.n_perm_blocks == 1;
+    const bool emit = !few_perms && keep && pair_lo == 0 && pair_hi == total && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
                       (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
     int pc_mode = emit ? PRECOUNT_NO : precount_mode(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget);
+    if (few_perms && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;  // the split-carrier kernel is the better form there
     if (pc_mode == PRECOUNT_SAMPLE) {
       // how much of a partner row is already in its upstream row: 2,048 pairs spread over the join (~40 us incl. the read-back)
       JoinParams q;
@@ -1561,7 +1565,8 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
       sp.unit_begin = p;
       sp.n_units = pe - p;
       CK(cudaMemsetAsync(ex->d_scalars + 2, 0, 2 * sizeof(unsigned), ex->stream));
-      CK(launch_join_sparse(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
+      if (sparse_sc_applies(jp, sp)) CK(launch_join_sparse_sc(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
+      else CK(launch_join_sparse(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
       LAUNCHED();
       launches++;
     } else {
@@ -1639,6 +1644,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     opts->kernel_used = kernel;
     opts->launches = launches;
     opts->precounted = sp.pcnt1 != nullptr;
+    opts->split_carrier = kernel == GCRE_KERNEL_SPARSE && sparse_sc_applies(jp, sp);
   }
   return GCRE_OK;
 }

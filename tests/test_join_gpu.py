@@ -92,6 +92,8 @@ def test_schedule_matches_oracle(engine, oracles, method, shape, kernel):
         if kernel == _lib.KERNEL_SPARSE and w.net.levels[lvl].n_pairs > 0 and lvl in ("1b", "4", "5"):
             # (joins that keep their rows emit the rows' counts for the next level instead, in the delta form)
             assert got[lvl].info["precounted"] == isinstance(kernel, _Precount), "GCRE_TEST_PRECOUNT must select the kernel form"
+        if kernel == _lib.KERNEL_SPARSE and not isinstance(kernel, _Precount) and w.net.levels[lvl].n_pairs > 0:
+            assert got[lvl].info["split_carrier"] == (perms <= 128), "<= 128 permutations run the split-carrier form"
 
 
 @pytest.mark.parametrize("pc", PC_MODES)
@@ -364,12 +366,13 @@ def test_many_permutations_span_several_blocks(engine, oracles, method, kernel):
         helpers.assert_same_results(got[lvl], want[lvl], what=f"{method} L{lvl}")
 
 
+@pytest.mark.parametrize("perms", [300, 96])
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("method", ["method1", "method2"])
-def test_dense_carrier_rows(engine, oracles, method, kernel):
+def test_dense_carrier_rows(engine, oracles, method, kernel, perms):
     """Common variants (up to half of the patients carry each gene): partner deltas of several hundred carriers exercise
     the plane-batch overflow (> 248 carriers between flushes) and the carrier-queue drain of the sparse kernel."""
-    w = synth.make_workload(600, 630, 40, 110, 300, seed=505, max_path_length=4, real_table=True, max_freq=0.5, zero_frac=0.0)
+    w = synth.make_workload(600, 630, 40, 110, perms, seed=505, max_path_length=4, real_table=True, max_freq=0.5, zero_frac=0.0)
     assert np.unpackbits(w.gene_bits.view(np.uint8), axis=1).sum(axis=1).max() > 400
     want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 4, 6)
     got, kept, _ = run_engine(engine, w, method, 4, 6, kernel)
@@ -380,13 +383,15 @@ def test_dense_carrier_rows(engine, oracles, method, kernel):
         assert got[lvl].info["kernel"] == kernel
 
 
+@pytest.mark.parametrize("perms", [300, 100])
 @pytest.mark.parametrize("pc", PC_MODES)
 @pytest.mark.parametrize("method", ["method1", "method2"])
-def test_wide_carrier_indices(engine, oracles, method, pc, monkeypatch):
+def test_wide_carrier_indices(engine, oracles, method, pc, perms, monkeypatch):
     """Cohorts above 65,535 patients use 32-bit carrier indices in the sparse kernel's lists; GCRE_TEST_WIDE_CARRIERS
     forces that code path on a cohort the oracle can check."""
     monkeypatch.setenv("GCRE_TEST_WIDE_CARRIERS", "1")
-    w = synth.make_workload(300, 310, 120, 400, 300, seed=606, max_path_length=5, real_table=True, max_freq=0.3, zero_frac=0.2)
+    # (perms = 100: the split-carrier kernel for <= 128 permutations, join_sparse_sc.cuh, in its delta form)
+    w = synth.make_workload(300, 310, 120, 400, perms, seed=606, max_path_length=5, real_table=True, max_freq=0.3, zero_frac=0.2)
     want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 5, 7)
     got, kept, _ = run_engine(engine, w, method, 5, 7, _lib.KERNEL_SPARSE)
     for k in kept_want:
@@ -435,13 +440,14 @@ def test_resident_join_index_matches_one_shot(engine):
         assert ra.info["pairs"] == rb.info["pairs"] > 0
 
 
+@pytest.mark.parametrize("perms", [300, 64])
 @pytest.mark.parametrize("pc", PC_MODES)
 @pytest.mark.parametrize("method", ["method1", "method2"])
-def test_sparse_queue_drain_corner_cases(engine, oracles, method, pc):
+def test_sparse_queue_drain_corner_cases(engine, oracles, method, pc, perms):
     """Hand-built rows that hit the carrier-queue edge cases of the sparse kernel: exactly 64 new carriers followed by list
     entries that are all already in the upstream row (a mid-list drain, then nothing left to drain but counts still in the
     bit planes), 65 new carriers, and a partner that adds nothing."""
-    n_cases, n_ctrls, perms = 230, 170, 300
+    n_cases, n_ctrls = 230, 170
     n = n_cases + n_ctrls
     def row(*ranges):
         v = np.zeros(n, dtype=np.int32)
