@@ -10,8 +10,15 @@ This is host-side post-processing of <= K * L * 2(L-1) sub-paths - not part of t
 the number of redrawn carriers that fall among the cases matters, and that number is hypergeometric, so besides the
 reference's Monte-Carlo estimate (`n_permutations` redraws; R's `sample()` stream cannot be reproduced, a seeded numpy
 generator is used) the exact limit of that estimate is available (`n_permutations=None`): the tail probability is summed
-over the support of the (independent) positive and negative hypergeometric counts.  Stratified resampling
-(R/DecoratedPvalue.R:229-262) is not implemented.
+over the support of the (independent) positive and negative hypergeometric counts.
+
+Stratified resampling (`strata=`, R/DecoratedPvalue.R:236-268): the added carriers are redrawn inside their own stratum.
+Per stratum the pool is the stratum minus every carrier of the sub-path (positive or negative part); as many patients as
+the gene adds positive carriers in that pool are drawn, then - from what is left of the pool - as many as it adds negative
+carriers.  So per stratum the case count of the positive draw is hypergeometric and that of the negative draw is
+hypergeometric given the first; the strata are independent and their counts add up.  The Monte-Carlo mode samples exactly
+that; the exact mode convolves the per-stratum joint distributions.  (Added carriers that sit in the other part of the
+sub-path belong to no pool and are not redrawn, as in the reference.)
 """
 from __future__ import annotations
 
@@ -45,11 +52,44 @@ class DecoratedResult:
     score: float
 
 
+def _stratified_counts(pool_case, pool_ctrl, k_pos, k_neg, n_permutations, rng):
+    """Monte-Carlo (cp, cn) totals over strata: per stratum cp_g ~ Hyp(cases, ctrls, k_pos_g); the negatives are drawn from
+    what is left and count CONTROLS: cn_g ~ Hyp(ctrls - (k_pos_g - cp_g), cases - cp_g, k_neg_g)."""
+    cp = np.zeros(n_permutations, dtype=np.int64)
+    cn = np.zeros(n_permutations, dtype=np.int64)
+    for c, d, kp, kn in zip(pool_case, pool_ctrl, k_pos, k_neg):
+        cpg = rng.hypergeometric(c, d, kp, size=n_permutations) if kp else np.zeros(n_permutations, dtype=np.int64)
+        cp += cpg
+        if kn:
+            good, bad = d - (kp - cpg), c - cpg
+            cn += rng.hypergeometric(good, bad, kn)
+    return cp, cn
+
+
+def _stratified_joint_pmf(pool_case, pool_ctrl, k_pos, k_neg):
+    """Exact joint distribution P[cp, cn] of the totals (2-D convolution of the per-stratum joints)."""
+    joint = np.ones((1, 1))
+    for c, d, kp, kn in zip(pool_case, pool_ctrl, k_pos, k_neg):
+        g = np.zeros((kp + 1, kn + 1))
+        xp, pp = _hypergeom_pmf(c, d, kp)
+        for x, px in zip(xp, pp):
+            xn, pn = _hypergeom_pmf(d - (kp - x), c - x, kn)
+            g[x, xn] += px * pn
+        out = np.zeros((joint.shape[0] + kp, joint.shape[1] + kn))
+        for i in range(kp + 1):  # strata are few and their draws small: a direct convolution is plenty
+            for j in range(kn + 1):
+                if g[i, j]:
+                    out[i:i + joint.shape[0], j:j + joint.shape[1]] += g[i, j] * joint
+        joint = out
+    return joint
+
+
 def compute_decorated_pvalue(pos1, neg1, pos2, neg2, n_cases: int, n_ctrls: int, method: int, value_table: np.ndarray,
-                             n_permutations: int | None = None, rng: np.random.Generator | None = None) -> DecoratedResult:
+                             n_permutations: int | None = None, rng: np.random.Generator | None = None, strata=None) -> DecoratedResult:
     """computeDecoratedPvalue (R/DecoratedPvalue.R:198-304) for boolean patient vectors (cases first).
 
     pos1/neg1: carriers of the sub-path (positive / negative part); pos2/neg2: carriers of the gene being added.
+    strata: optional stratum label per patient (the `stratum` column of the reference's strata file, in patient order).
     """
     pos1, neg1, pos2, neg2 = (np.asarray(v, dtype=bool) for v in (pos1, neg1, pos2, neg2))
     n = n_cases + n_ctrls
@@ -74,7 +114,30 @@ def compute_decorated_pvalue(pos1, neg1, pos2, neg2, n_cases: int, n_ctrls: int,
     # pools the carriers are redrawn from (R/DecoratedPvalue.R:232-233): everything outside the sub-path
     good_pos, bad_pos = int((~pos1 & is_case).sum()), int((~pos1 & ~is_case).sum())    # "good" = a case
     good_neg, bad_neg = int((~neg1 & ~is_case).sum()), int((~neg1 & is_case).sum())    # "good" = a control
-    if n_permutations is None:
+    if strata is not None:
+        strata = np.asarray(strata)
+        if strata.shape[0] != n:
+            raise ValueError("one stratum label per patient is required")
+        free = ~(pos1 | neg1)  # R/DecoratedPvalue.R:240-242: the stratum minus every carrier of the sub-path
+        groups = list(dict.fromkeys(strata.tolist()))  # unique(), in order of appearance (R/DecoratedPvalue.R:80)
+        pool_case = [int((free & (strata == g) & is_case).sum()) for g in groups]
+        pool_ctrl = [int((free & (strata == g) & ~is_case).sum()) for g in groups]
+        kp = [int((pos2 & free & (strata == g)).sum()) for g in groups]
+        kn = [int((neg2 & free & (strata == g)).sum()) for g in groups]
+        for c, d, a_, b_ in zip(pool_case, pool_ctrl, kp, kn):
+            if a_ + b_ > c + d:  # R's sample() stops with "cannot take a sample larger than the population"
+                raise ValueError("a stratum has fewer free patients than carriers to redraw")
+        tp, tn = sum(kp), sum(kn)  # (carriers outside every pool are not redrawn)
+        if n_permutations is None:
+            joint = _stratified_joint_pmf(pool_case, pool_ctrl, kp, kn)
+            cp_ax, cn_ax = np.arange(joint.shape[0]), np.arange(joint.shape[1])
+            sc = score_of(cp_ax[:, None], tp, cn_ax[None, :], tn)
+            pvalue = float(joint[(sc >= score) & (joint > 0)].sum())
+        else:
+            rng = rng or np.random.default_rng(0)
+            cp, cn = _stratified_counts(pool_case, pool_ctrl, kp, kn, n_permutations, rng)
+            pvalue = float((score_of(cp, tp, cn, tn) >= score).mean())
+    elif n_permutations is None:
         xp, pp = _hypergeom_pmf(good_pos, bad_pos, k_pos)
         xn, pn = _hypergeom_pmf(good_neg, bad_neg, k_neg)
         s = score_of(xp[:, None], k_pos, xn[None, :], k_neg)
@@ -88,7 +151,7 @@ def compute_decorated_pvalue(pos1, neg1, pos2, neg2, n_cases: int, n_ctrls: int,
 
 
 def decorated_pvalues_for_path(gene_rows: np.ndarray, signs, n_cases: int, n_ctrls: int, method: int, value_table: np.ndarray,
-                               n_permutations: int | None = None, rng: np.random.Generator | None = None) -> list[dict]:
+                               n_permutations: int | None = None, rng: np.random.Generator | None = None, strata=None) -> list[dict]:
     """All forward and backward splits of one path (R/DecoratedPvalue.R:123-180).
 
     gene_rows: bool/0-1 array [L][n] of the path's genes in order; signs: +1/-1 per gene (method 2 moves the genes with a
@@ -104,9 +167,9 @@ def decorated_pvalues_for_path(gene_rows: np.ndarray, signs, n_cases: int, n_ctr
         pos[signs == -1] = False
     out = []
     for j in range(1, L):  # forward: genes 1..j, then gene j+1
-        r = compute_decorated_pvalue(pos[:j].any(0), neg[:j].any(0), pos[j], neg[j], n_cases, n_ctrls, method, value_table, n_permutations, rng)
+        r = compute_decorated_pvalue(pos[:j].any(0), neg[:j].any(0), pos[j], neg[j], n_cases, n_ctrls, method, value_table, n_permutations, rng, strata)
         out.append({"direction": "Forward", "subpath1": list(range(j)), "subpath2": j, **r.__dict__})
     for j in range(L - 1, 0, -1):  # backward: genes L..j+1, then gene j
-        r = compute_decorated_pvalue(pos[j:].any(0), neg[j:].any(0), pos[j - 1], neg[j - 1], n_cases, n_ctrls, method, value_table, n_permutations, rng)
+        r = compute_decorated_pvalue(pos[j:].any(0), neg[j:].any(0), pos[j - 1], neg[j - 1], n_cases, n_ctrls, method, value_table, n_permutations, rng, strata)
         out.append({"direction": "Backward", "subpath1": list(range(L - 1, j - 1, -1)), "subpath2": j - 1, **r.__dict__})
     return out
