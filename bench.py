@@ -248,14 +248,39 @@ def run_reference_arm(a):
             "cpu_baseline": {"value": value, "unit": "pair*perm/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": value, "unit": "pair*perm/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": round(time.time() - t0, 1)}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL ("NCCL version ..."), the reference's printf progress lines and any
+    library chatter also write to file descriptor 1, so fd 1 is pointed at stderr for the whole run and the JSON line is
+    written to the saved original descriptor at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     a = parse_args()
+    claim_stdout()
     if a.impl == "reference":
         return run_reference_arm(a)
 
@@ -677,7 +702,7 @@ def main():
                 "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu, "per_level": per_level,
                 "pair_perm_per_step": pp_step, "workload_gen_s": round(gen_s, 1)}
-        print(json.dumps(line))
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
