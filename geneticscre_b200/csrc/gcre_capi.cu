@@ -1430,8 +1430,8 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     if (const char* mb = std::getenv("GCRE_PRECOUNT_MAX_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
     // kept rows take their counts along (join_sparse.cuh) when the join writes all of them; GCRE_TEST_EMIT=0 (test hook) turns it off
     const char* emit_env = std::getenv("GCRE_TEST_EMIT");
-    // <= 128 permutations: the split-carrier kernel (join_sparse_sc.cuh) runs instead and neither writes nor reads count tables
-    const bool few_perms = ex->Ip <= sparse_sc::MAX_PERMS && sp.n_perm_blocks == 1;
+    // <= 512 permutations: the split-carrier kernel (join_sparse_sc.cuh) runs instead and neither writes nor reads count tables
+    const bool few_perms = sparse_sc_enabled(ex->Ip, sp.n_perm_blocks);
     const bool emit = !few_perms && keep && pair_lo == 0 && pair_hi == total && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
                       (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
     int pc_mode = emit ? PRECOUNT_NO : precount_mode(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget);

@@ -1,12 +1,13 @@
-// Sparse join for FEW permutations (<= 128, e.g. GWASPA's default of 100): the carriers of one pair are split across the
+// Sparse join for FEW permutations (<= 512, e.g. GWASPA's default of 100): the carriers of one pair are split across the
 // lanes of the warp.
 //
 // join_sparse_kernel gives every lane one 32-permutation word of the patient-major masks; with <= 128 permutations only 4
-// of the 32 lanes have a word and 28 idle through the gathers, the flush and the look-ups.  Here the warp is 8 sub-groups
-// (s = lane >> 2) x 4 words (w = lane & 3): sub-group s walks every eighth group of carriers of the SAME pair, so a batch of
-// 64 carriers costs each lane eight gathers; the eight partial count vectors of a word are then combined with a
-// reduce-scatter over shuffles (3 rounds, 14 shuffles), which leaves lane (w, s) with the counts of the four permutations
-// w*32 + {s, s+8, s+16, s+24} - the only ones it looks up and keeps a running maximum for.  Same integers as every other
+// of the 32 lanes have a word and 28 idle through the gathers, the flush and the look-ups (8 of 32 busy up to 256, 16 up to
+// 512).  Here the warp is G = 32 / NW sub-groups x NW words (NW = 4, 8, 16; w = lane % NW, s = lane / NW): sub-group s walks
+// every G-th group of eight carriers of the SAME pair, so a batch of 8 G carriers costs each lane eight gathers; the G partial
+// count vectors of a word are then combined with a reduce-scatter over shuffles (log2 G rounds), which leaves lane (w, s)
+// with 16 / G of the 16 packed count registers - for NW = 4 the counts of the four permutations w*32 + {s, s+8, s+16, s+24} -
+// the only ones it looks up and keeps a running maximum for.  Same integers as every other
 // kernel, so results are bit-identical.  (Splitting the warp over different PARTNERS instead was tried first and lost to
 // the heavy-tailed list lengths; splitting one pair's carriers has no such imbalance.)
 //
@@ -21,47 +22,67 @@ namespace gcre {
 namespace sparse_sc {
 constexpr int THREADS = 128;
 constexpr int WARPS = THREADS / 32;
-constexpr int QCAP = 128;       // two batches of 64: one being filled while < 64 entries wait
-constexpr int MIN_BLOCKS = 8;
-constexpr int MAX_PERMS = 128;  // 4 words of 32
+constexpr int QCAP = 128;       // the batch being drained (<= 64 slots) + the < 32 entries that can wait behind it, in whole batches
+constexpr int MAX_PERMS = 512;  // 16 words of 32
+constexpr int min_blocks(int nw) { return nw == 16 ? 6 : 8; }
 }  // namespace sparse_sc
 
-// position of the t-th queued carrier: inside its batch of 64 the entries of sub-group s = t % 8 are contiguous (two 16-byte
-// shared loads per lane and batch)
-__device__ __forceinline__ uint32_t sc_slot(uint32_t t) { return (t & ~63u) + ((t & 7u) << 3) + ((t & 63u) >> 3); }
+// position of the t-th queued carrier: inside its batch of B = 8 G the entries of sub-group s = t % G are contiguous (two
+// 16-byte shared loads per lane and batch)
+template <int G>
+__device__ __forceinline__ uint32_t sc_slot(uint32_t t) {
+  constexpr uint32_t B = 8 * G;
+  return (t / B) * B + ((t % G) << 3) + ((t % B) / G);
+}
 
-// 16 packed count registers per lane (partial sums over the lane's share of the carriers) -> the two registers 2s, 2s+1 summed
-// over the 8 sub-groups of the lane's word
-__device__ __forceinline__ void sc_reduce_scatter(const uint32_t (&c16)[16], int lane, uint32_t (&out)[2]) {
-  const bool b2 = (lane & 16) != 0, b1 = (lane & 8) != 0, b0 = (lane & 4) != 0;
-  uint32_t r8[8], r4[4];
+// 16 packed count registers per lane (partial sums over the lane's share of the carriers) -> the R = NW / 2 registers
+// R*s .. R*s + R-1 summed over the G sub-groups of the lane's word (s = lane / NW)
+template <int NW>
+__device__ __forceinline__ void sc_reduce_scatter(const uint32_t (&c16)[16], int lane, uint32_t (&out)[NW / 2]) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+  uint32_t r8[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    const uint32_t send = b2 ? c16[k] : c16[k + 8], keep = b2 ? c16[k + 8] : c16[k];
+    const uint32_t send = b4 ? c16[k] : c16[k + 8], keep = b4 ? c16[k + 8] : c16[k];
     r8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
   }
+  if constexpr (NW == 16) {
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const uint32_t send = b1 ? r8[k] : r8[k + 4], keep = b1 ? r8[k + 4] : r8[k];
-    r4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
+    for (int k = 0; k < 8; k++) out[k] = r8[k];
+  } else {
+    uint32_t r4[4];
 #pragma unroll
-  for (int k = 0; k < 2; k++) {
-    const uint32_t send = b0 ? r4[k] : r4[k + 2], keep = b0 ? r4[k + 2] : r4[k];
-    out[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    for (int k = 0; k < 4; k++) {
+      const uint32_t send = b3 ? r8[k] : r8[k + 4], keep = b3 ? r8[k + 4] : r8[k];
+      r4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    if constexpr (NW == 8) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) out[k] = r4[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const uint32_t send = b2 ? r4[k] : r4[k + 2], keep = b2 ? r4[k + 2] : r4[k];
+        out[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    }
   }
 }
 
-template <int M, bool KEEP, typename CT>
-__global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) join_sparse_sc_kernel(const JoinParams a, const SparseParams s) {
+template <int M, bool KEEP, typename CT, int NW>
+__global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW)) join_sparse_sc_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse_sc;
   constexpr int PB = sparse::PB, FLUSH_AT = sparse::FLUSH_AT;
+  constexpr int G = 32 / NW;          // sub-groups sharing one pair's carriers
+  constexpr uint32_t B = 8 * G;       // carriers per batch
+  constexpr int R = NW / 2;           // packed count registers (2 permutations each) a lane keeps after the reduce-scatter
+  constexpr int NCOPY = (B == 64) ? 2 : 1;  // 32-slot pieces that can hold the < 32 entries left behind a drained batch
   const CT* car0 = static_cast<const CT*>(s.car0);
   const CT* car1 = static_cast<const CT*>(s.car1);
   __shared__ __align__(16) uint32_t s_queue[WARPS][QCAP];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w = lane & 3, sub = lane >> 2;
+  const int w = lane % NW, sub = lane / NW;
   const int Wp = a.Wp, Iw = a.Iw;
   const int row_words = Wp * M;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -69,10 +90,10 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
   const uint32_t* pt_lane = a.pt + w;
   const uint32_t zero_row = (uint32_t)s.n * (uint32_t)Iw;
 
-  // permutations of this lane: r = w*32 + sub + 8*j, j = 0..3  <->  (register 2*sub + (j >> 1), half j & 1)
-  float best[4];
+  // permutations of this lane: (register i = R*sub + k, half hf)  <->  bit ((i & 1)*2 + hf)*8 + (i >> 1) of word w
+  float best[2 * R];
 #pragma unroll
-  for (int j = 0; j < 4; j++) best[j] = 0.0f;
+  for (int j = 0; j < 2 * R; j++) best[j] = 0.0f;
 
   while (true) {
     unsigned long long g = 0;
@@ -103,9 +124,13 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
     };
 
     // ---- base: the upstream row's own carriers, 64 per step, sub-group `sub` takes the sub-th group of eight ----
-    uint32_t t0[M], nc0[M], base[M][2];
+    uint32_t t0[M], nc0[M], base[M][R];
 #pragma unroll
-    for (int h = 0; h < M; h++) t0[h] = nc0[h] = base[h][0] = base[h][1] = 0;
+    for (int h = 0; h < M; h++) {
+      t0[h] = nc0[h] = 0;
+#pragma unroll
+      for (int k = 0; k < R; k++) base[h][k] = 0;
+    }
 #pragma unroll 1
     for (int h = 0; h < M; h++) {
       uint32_t acc[16];
@@ -115,7 +140,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
       const uint32_t o = s.off0[item], plen = s.off0[item + 1] - o;
       const uint32_t t0h = s.len0[item], nc0h = s.ncase0[item];
 #pragma unroll 1
-      for (uint32_t i = 0; i < plen; i += 64) {
+      for (uint32_t i = 0; i < plen; i += B) {
         uint32_t x[8];
         if (i + sub * 8 < plen) {
           uint32_t c[8];
@@ -126,12 +151,19 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
 #pragma unroll
           for (int q = 0; q < 8; q++) x[q] = 0u;
         }
-        acc8(acc, x, 8, i + 64 >= plen);
+        acc8(acc, x, 8, i + B >= plen);
       }
-      uint32_t r2[2];
-      sc_reduce_scatter(acc, lane, r2);
-      if (M == 1 || h == 0) { t0[0] = t0h; nc0[0] = nc0h; base[0][0] = r2[0]; base[0][1] = r2[1]; }
-      else { t0[M - 1] = t0h; nc0[M - 1] = nc0h; base[M - 1][0] = r2[0]; base[M - 1][1] = r2[1]; }
+      uint32_t rr[R];
+      sc_reduce_scatter<NW>(acc, lane, rr);
+      if (M == 1 || h == 0) {
+        t0[0] = t0h; nc0[0] = nc0h;
+#pragma unroll
+        for (int k = 0; k < R; k++) base[0][k] = rr[k];
+      } else {
+        t0[M - 1] = t0h; nc0[M - 1] = nc0h;
+#pragma unroll
+        for (int k = 0; k < R; k++) base[M - 1][k] = rr[k];
+      }
     }
 
     bool base_done = false;
@@ -140,9 +172,13 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
       const uint32_t loc = loc0 + j;
       bool flip = true;
       if (M == 2) flip = need_flip(a.path_length, a.signs, idx, loc);
-      uint32_t nd[M], ncn[M], cnt[M][2];
+      uint32_t nd[M], ncn[M], cnt[M][R];
 #pragma unroll
-      for (int h = 0; h < M; h++) nd[h] = ncn[h] = cnt[h][0] = cnt[h][1] = 0;
+      for (int h = 0; h < M; h++) {
+        nd[h] = ncn[h] = 0;
+#pragma unroll
+        for (int k = 0; k < R; k++) cnt[h][k] = 0;
+      }
 #pragma unroll 1
       for (int h = 0; h < M; h++) {
         uint32_t c16[16];
@@ -163,16 +199,16 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
           const bool keep = valid && !((w0 >> (c & 31)) & 1u);
           const unsigned km = __ballot_sync(0xffffffffu, keep);
           ncnh += __popc(__ballot_sync(0xffffffffu, keep && (int)c < a.n_cases));
-          if (keep) queue[sc_slot(qn + __popc(km & lt_mask))] = c * (uint32_t)Iw;
+          if (keep) queue[sc_slot<G>(qn + __popc(km & lt_mask))] = c * (uint32_t)Iw;
           qn += __popc(km);
           const bool last_chunk = i0 + 32 >= len;
-          // drain whole batches of 64; after the last chunk also the remainder (padded with the zero row), and at least once
+          // drain whole batches of B; after the last chunk also the remainder (padded with the zero row), and at least once
           // when counts of an earlier batch are still in the planes
 #pragma unroll 1
-          while (qn >= 64 || (last_chunk && (qn > 0 || inbatch > 0))) {
-            const uint32_t real = min(qn, 64u);
-            if (real < 64) {
-              for (uint32_t t = real + lane; t < 64; t += 32) queue[sc_slot(t)] = zero_row;
+          while (qn >= B || (last_chunk && (qn > 0 || inbatch > 0))) {
+            const uint32_t real = min(qn, B);
+            if (real < B) {
+              for (uint32_t t = real + lane; t < B; t += 32) queue[sc_slot<G>(t)] = zero_row;
             }
             __syncwarp();
             uint32_t x[8];
@@ -185,24 +221,33 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
             x[5] = __ldg(pt_lane + hi.y);
             x[6] = __ldg(pt_lane + hi.z);
             x[7] = __ldg(pt_lane + hi.w);
-            const uint32_t rem = qn - real;                      // < 64 entries waiting in the second batch
-            acc8(c16, x, (int)((real + 7u) >> 3), last_chunk && rem == 0);
-            // the second batch moves to the front (slot layout is per batch, so a plain copy of its 64 slots)
-            const uint32_t m0 = queue[64 + lane], m1 = queue[96 + lane];
+            const uint32_t rem = qn - real;                      // < 32 entries waiting behind the drained batch
+            acc8(c16, x, (int)((real + G - 1) / G), last_chunk && rem == 0);
+            // they move to the front: the slot layout is per batch, so whole batches are copied as they are
+            uint32_t mv[NCOPY];
+#pragma unroll
+            for (int k = 0; k < NCOPY; k++) mv[k] = queue[B + 32 * k + lane];
             __syncwarp();
             if (rem) {
-              queue[lane] = m0;
-              queue[32 + lane] = m1;
+#pragma unroll
+              for (int k = 0; k < NCOPY; k++) queue[32 * k + lane] = mv[k];
             }
             __syncwarp();
             ndh += real;
             qn = rem;
           }
         }
-        uint32_t r2[2];
-        sc_reduce_scatter(c16, lane, r2);
-        if (M == 1 || h == 0) { nd[0] = ndh; ncn[0] = ncnh; cnt[0][0] = base[0][0] + r2[0]; cnt[0][1] = base[0][1] + r2[1]; }
-        else { nd[M - 1] = ndh; ncn[M - 1] = ncnh; cnt[M - 1][0] = base[M - 1][0] + r2[0]; cnt[M - 1][1] = base[M - 1][1] + r2[1]; }
+        uint32_t rr[R];
+        sc_reduce_scatter<NW>(c16, lane, rr);
+        if (M == 1 || h == 0) {
+          nd[0] = ndh; ncn[0] = ncnh;
+#pragma unroll
+          for (int k = 0; k < R; k++) cnt[0][k] = base[0][k] + rr[k];
+        } else {
+          nd[M - 1] = ndh; ncn[M - 1] = ncnh;
+#pragma unroll
+          for (int k = 0; k < R; k++) cnt[M - 1][k] = base[M - 1][k] + rr[k];
+        }
       }
 
       bool empty = nd[0] == 0;
@@ -213,7 +258,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
           const unsigned total = t0[0] + nd[0];
           const float* row = a.diagF + diag_base(total);
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
+          for (int q = 0; q < 2 * R; q++) {
             const uint32_t v = cnt[0][q >> 1];
             const uint32_t c = (q & 1) ? (v >> 16) : (v & 0xffffu);
             best[q] = fmaxf(best[q], __ldg(row + c));
@@ -223,7 +268,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
           const double* rowp = a.diagDM + diag_base(tp);
           const double* rown = a.diagDM + diag_base(tn) + tn;
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
+          for (int q = 0; q < 2 * R; q++) {
             const uint32_t vp = cnt[0][q >> 1], vn = cnt[M - 1][q >> 1];
             const uint32_t cp = (q & 1) ? (vp >> 16) : (vp & 0xffffu);
             const uint32_t cn = (q & 1) ? (vn >> 16) : (vn & 0xffffu);
@@ -295,36 +340,46 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::MIN_BLOCKS) joi
     }
     __syncwarp();
   }
-  // lane (w, sub) owns permutations w*32 + sub + 8*q
+  // best[q]: register i = R*sub + (q >> 1), half q & 1  ->  permutation w*32 + ((i & 1)*2 + (q & 1))*8 + (i >> 1)
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int r = w * 32 + sub + 8 * q;
+  for (int q = 0; q < 2 * R; q++) {
+    const int i = R * sub + (q >> 1);
+    const int r = w * 32 + ((i & 1) * 2 + (q & 1)) * 8 + (i >> 1);
     if (r < a.Ip && best[q] > 0.0f) atomicMax(a.perm_max + r, __float_as_int(best[q]));
   }
 }
 
-// few permutations, no count tables in play
+// few permutations, no count tables in play; GCRE_TEST_NO_SPLIT=1 (test hook) keeps the one-word-per-lane kernel
+static inline bool sparse_sc_enabled(int Ip, int n_perm_blocks) {
+  return Ip <= sparse_sc::MAX_PERMS && n_perm_blocks == 1 && std::getenv("GCRE_TEST_NO_SPLIT") == nullptr;
+}
 static inline bool sparse_sc_applies(const JoinParams& jp, const SparseParams& sp) {
-  return jp.Ip <= sparse_sc::MAX_PERMS && sp.n_perm_blocks == 1 && !sp.pcnt0 && !sp.pcnt1 && !sp.pcnt_res;
+  return sparse_sc_enabled(jp.Ip, sp.n_perm_blocks) && !sp.pcnt0 && !sp.pcnt1 && !sp.pcnt_res;
+}
+
+template <int M, bool KEEP, int NW>
+static inline void launch_sparse_sc_ct(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int sm_count) {
+  const unsigned long long want = (sp.n_units + sparse_sc::WARPS - 1) / sparse_sc::WARPS;
+  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * sparse_sc::min_blocks(NW));
+  if (sparse_wide(sp.n)) join_sparse_sc_kernel<M, KEEP, uint32_t, NW><<<grid, sparse_sc::THREADS, 0, stream>>>(jp, sp);
+  else join_sparse_sc_kernel<M, KEEP, uint16_t, NW><<<grid, sparse_sc::THREADS, 0, stream>>>(jp, sp);
 }
 
 template <int M, bool KEEP>
-static inline void launch_sparse_sc_ct(unsigned grid, cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, bool wide) {
-  if (wide) join_sparse_sc_kernel<M, KEEP, uint32_t><<<grid, sparse_sc::THREADS, 0, stream>>>(jp, sp);
-  else join_sparse_sc_kernel<M, KEEP, uint16_t><<<grid, sparse_sc::THREADS, 0, stream>>>(jp, sp);
+static inline void launch_sparse_sc_nw(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int sm_count) {
+  if (jp.Ip <= 128) launch_sparse_sc_ct<M, KEEP, 4>(stream, jp, sp, sm_count);
+  else if (jp.Ip <= 256) launch_sparse_sc_ct<M, KEEP, 8>(stream, jp, sp, sm_count);
+  else launch_sparse_sc_ct<M, KEEP, 16>(stream, jp, sp, sm_count);
 }
 
 static inline cudaError_t launch_join_sparse_sc(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count) {
   if (sp.n_units == 0) return cudaSuccess;
-  const unsigned long long want = (sp.n_units + sparse_sc::WARPS - 1) / sparse_sc::WARPS;
-  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * sparse_sc::MIN_BLOCKS);
-  const bool wide = sparse_wide(sp.n);
   if (M == 1) {
-    if (keep) launch_sparse_sc_ct<1, true>(grid, stream, jp, sp, wide);
-    else launch_sparse_sc_ct<1, false>(grid, stream, jp, sp, wide);
+    if (keep) launch_sparse_sc_nw<1, true>(stream, jp, sp, sm_count);
+    else launch_sparse_sc_nw<1, false>(stream, jp, sp, sm_count);
   } else {
-    if (keep) launch_sparse_sc_ct<2, true>(grid, stream, jp, sp, wide);
-    else launch_sparse_sc_ct<2, false>(grid, stream, jp, sp, wide);
+    if (keep) launch_sparse_sc_nw<2, true>(stream, jp, sp, sm_count);
+    else launch_sparse_sc_nw<2, false>(stream, jp, sp, sm_count);
   }
   return cudaGetLastError();
 }

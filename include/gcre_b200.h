@@ -83,7 +83,7 @@ typedef struct {
   int32_t kernel_used;      /* out: gcre_kernel actually run */
   int32_t launches;         /* out: kernel launches made by this call */
   int32_t precounted;       /* out: 1 when the sparse kernel ran in its pre-counted-partner form (join_sparse.cuh) */
-  int32_t split_carrier;    /* out: 1 when the <= 128-permutation form of the sparse kernel ran (join_sparse_sc.cuh) */
+  int32_t split_carrier;    /* out: 1 when the <= 512-permutation form of the sparse kernel ran (join_sparse_sc.cuh) */
 } gcre_join_opts;
 
 const char* gcre_last_error(void);

@@ -20,8 +20,15 @@ class _Precount(int):
     delta kernels, so both families run on every shape whatever the cost model would pick."""
 
 
+class _NoSplit(int):
+    """KERNEL_SPARSE with the split-carrier form for <= 512 permutations switched off (GCRE_TEST_NO_SPLIT=1), so the
+    one-word-per-lane kernel - delta form, counts handed from level to level - runs on the small shapes too."""
+
+
 SPARSE_PC = _Precount(_lib.KERNEL_SPARSE)
-KERNELS = [pytest.param(_lib.KERNEL_DENSE, id="dense"), pytest.param(_lib.KERNEL_SPARSE, id="sparse"), pytest.param(SPARSE_PC, id="sparse_pc")]
+SPARSE_NOSPLIT = _NoSplit(_lib.KERNEL_SPARSE)
+KERNELS = [pytest.param(_lib.KERNEL_DENSE, id="dense"), pytest.param(_lib.KERNEL_SPARSE, id="sparse"), pytest.param(SPARSE_PC, id="sparse_pc"),
+           pytest.param(SPARSE_NOSPLIT, id="sparse_nosplit")]
 PC_MODES = [pytest.param("0", id="delta"), pytest.param("1", id="precount")]
 
 
@@ -33,6 +40,8 @@ def _precount_mode(request, monkeypatch):
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", "1")
     elif k == _lib.KERNEL_SPARSE:
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", "0")
+    if isinstance(k, _NoSplit):
+        monkeypatch.setenv("GCRE_TEST_NO_SPLIT", "1")
     if "pc" in params:
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", params["pc"])
 
@@ -93,7 +102,7 @@ def test_schedule_matches_oracle(engine, oracles, method, shape, kernel):
             # (joins that keep their rows emit the rows' counts for the next level instead, in the delta form)
             assert got[lvl].info["precounted"] == isinstance(kernel, _Precount), "GCRE_TEST_PRECOUNT must select the kernel form"
         if kernel == _lib.KERNEL_SPARSE and not isinstance(kernel, _Precount) and w.net.levels[lvl].n_pairs > 0:
-            assert got[lvl].info["split_carrier"] == (perms <= 128), "<= 128 permutations run the split-carrier form"
+            assert got[lvl].info["split_carrier"] == (perms <= 512 and not isinstance(kernel, _NoSplit)), "<= 512 permutations run the split-carrier form"
 
 
 @pytest.mark.parametrize("pc", PC_MODES)
@@ -103,6 +112,7 @@ def test_schedule_without_emitted_counts(engine, oracles, method, pc, monkeypatc
     lists of its upstream operand); GCRE_TEST_EMIT=0 turns that off, so the in-kernel base walk and - with pre-counting
     forced - the KEEP form of the pre-counted kernels run on the full schedule too."""
     monkeypatch.setenv("GCRE_TEST_EMIT", "0")
+    monkeypatch.setenv("GCRE_TEST_NO_SPLIT", "1")  # (257 permutations would otherwise take the split-carrier form)
     shape = SHAPES[4]
     nc, nt, g, e, perms, top_k = shape
     w = synth.make_workload(nc, nt, g, e, perms, seed=4242, max_path_length=5, real_table=True, max_freq=0.12, zero_frac=0.3)
@@ -178,6 +188,7 @@ def test_precount_chosen_by_sampled_overlap(engine, oracles, method, monkeypatch
     GCRE_TEST_PRECOUNT=sample applies that rule to every score-only join here.  Level 1b (empty upstream rows: nothing shared)
     must come out pre-counted, level 4 of this schedule (partner shares a gene with the upstream path) must not."""
     monkeypatch.setenv("GCRE_TEST_PRECOUNT", "sample")
+    monkeypatch.setenv("GCRE_TEST_NO_SPLIT", "1")  # (the split-carrier form for <= 512 permutations never pre-counts)
     w = synth.make_workload(257, 300, 200, 800, 257, seed=4243, max_path_length=5, real_table=True, max_freq=0.12, zero_frac=0.3)
     want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 5, 8)
     got, kept, _ = run_engine(engine, w, method, 5, 8, _lib.KERNEL_SPARSE)
@@ -390,7 +401,7 @@ def test_wide_carrier_indices(engine, oracles, method, pc, perms, monkeypatch):
     """Cohorts above 65,535 patients use 32-bit carrier indices in the sparse kernel's lists; GCRE_TEST_WIDE_CARRIERS
     forces that code path on a cohort the oracle can check."""
     monkeypatch.setenv("GCRE_TEST_WIDE_CARRIERS", "1")
-    # (perms = 100: the split-carrier kernel for <= 128 permutations, join_sparse_sc.cuh, in its delta form)
+    # (both permutation counts take the split-carrier kernel, join_sparse_sc.cuh: 4 words for 100, 16 words for 300)
     w = synth.make_workload(300, 310, 120, 400, perms, seed=606, max_path_length=5, real_table=True, max_freq=0.3, zero_frac=0.2)
     want, kept_want, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, method, 5, 7)
     got, kept, _ = run_engine(engine, w, method, 5, 7, _lib.KERNEL_SPARSE)
