@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=2, choices=[1, 2],
                     help="e2e leg: 2 = submit the two methods from two host threads (uploads of one overlap joins of the other); 1 = sequential")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: max(10, --steps))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per method for the baseline sample")
     for k, v in WORKLOAD.items():
         ap.add_argument("--" + k.replace("_", "-"), type=type(v), default=v)
@@ -89,6 +90,18 @@ def workload_config(a, w):
         "l2_policy": "inputs larger than L2: path sets + tables per method exceed the 126 MB L2",
         "seed": a.seed,
     }
+
+
+def full_config(a, w, world):
+    """config of the JSON line - the same object in both arms (the reference arm describes its own run in cpu_baseline)."""
+    shard_perms = world > 1 and a.shard == "perms"
+    last = ["1a", "1b", "2", "3", "4", "5"][a.path_length]
+    cfg = workload_config(a, w)
+    cfg["permutations_total"] = w.n_perms * (world if shard_perms else 1)
+    cfg["parallelism"] = ("1 GPU" if world == 1 else
+                          f"{world} GPUs, one block of {w.n_perms} permutations per GPU over all pairs; maxima merged with one NCCL allreduce(max)" if shard_perms else
+                          f"{world} GPUs, level-{last} upstream rows sharded by pair count; one NCCL allreduce(max) per join + top-K gather")
+    return cfg
 
 
 def pairs_per_step(w, path_length):
@@ -148,82 +161,226 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU reference arm
 # ----------------------------------------------------------------------------------------------------------------------
+# The reference's JoinMethod has no virtual destructor (src/gcre.h:92-99) and its workers are held through
+# unique_ptr<JoinMethod>, so every method-2 worker's private (n+1)^2 clone of the value table (src/methods.h:128: 800 MB at
+# n = 10,000) is never freed: nthreads x 800 MB leak per method-2 join.  The unmodified reference therefore runs in WORKER
+# SUBPROCESSES that are replaced after a bounded number of joins (round 1's in-process arm was OOM-killed on the 1-GPU box).
+# The workers load only oracle/_ref/*.so; the process that owns the GPU never maps the reference, and the reference arm never
+# maps the CUDA engine.
+REF_JOINS_PER_WORKER = {"method1": 64, "method2": 2}
+
+
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 64 << 30
+
+
+def workload_file(w, a):
+    """The workload as an uncompressed .npz in shared memory (workers map it instead of regenerating it)."""
+    import tempfile
+
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    path = os.path.join(d, f"gcre_bench_workload_{os.getpid()}.npz")
+    net = w.net
+    np.savez(path, n_cases=w.n_cases, n_ctrls=w.n_ctrls, n_perms=w.n_perms, gene_bits=w.gene_bits, gene_bits2=w.gene_bits2,
+             perm_masks=w.perm_masks, value_table=w.value_table, n_genes=net.n_genes, edges_src=net.edges_src, edges_trg=net.edges_trg,
+             edges_sign=net.edges_sign, ents2=net.ents2, path_length=a.path_length)
+    return path
+
+
+def load_workload_file(path):
+    from geneticscre_b200 import synth
+
+    z = np.load(path, allow_pickle=False)
+    net = synth.network_from_edges(int(z["n_genes"]), z["edges_src"], z["edges_trg"], z["edges_sign"], ents2=z["ents2"],
+                                   max_path_length=max(int(z["path_length"]), 4))
+    return synth.Workload(int(z["n_cases"]), int(z["n_ctrls"]), int(z["n_perms"]), z["gene_bits"], z["gene_bits2"], z["perm_masks"],
+                          z["value_table"], net)
+
+
+def ref_worker_main(path, method, kind, threads, top_k):
+    """Worker process: the reference's own JoinExec (kind "reference") or the scalar restatement (kind "port") with levels
+    1-3 replayed once; then one level-4 join over the first x upstream rows per request line on stdin."""
+    from geneticscre_b200 import schedule
+    from oracle import pyoracle as po
+
+    real_out = os.dup(1)
+    os.dup2(2, 1)  # the reference printf()s progress lines on every join
+
+    def reply(obj):
+        os.write(real_out, (json.dumps(obj) + "\n").encode())
+
+    t0 = time.time()
+    w = load_workload_file(path)
+    if kind == "reference":
+        ex = po.RefExec(method, w.n_cases, w.n_ctrls, w.n_perms)
+        ex.nthreads = threads
+    else:
+        ex = po.OracleExec(method, w.n_cases, w.n_ctrls, w.n_perms)
+    ex.top_k = top_k
+    ex.setValueTable(w.value_table)
+    ex.setPermutedMasks(w.perm_masks)
+    _, kept = schedule.replay_levels(ex, po.UidRelSet, w, 3, only=())
+    p0, p1 = kept["paths3"], kept["paths2"]
+    lv = w.net.levels["4"]
+    csum = np.cumsum(lv.count.astype(np.int64))
+    reply({"ready": True, "setup_s": time.time() - t0})
+    for line in sys.stdin:
+        req = json.loads(line)
+        if req.get("quit"):
+            break
+        x = int(min(max(req["x"], 1), lv.n_uids))
+        uids = po.UidRelSet(4, lv.src[:x], lv.trg[:x], lv.count[:x], lv.location[:x], lv.signs[:x])
+        sub = p0 if x == lv.n_uids else p0.select(np.arange(x, dtype=np.int32))
+        t = time.time()
+        r = ex.join(uids, sub, p1, ex.createPathSet(0))
+        dt = time.time() - t
+        out = {"seconds": dt, "pairs": int(csum[x - 1]), "x": x}
+        if req.get("results"):
+            out["scores"] = [[s.score if np.isfinite(s.score) else repr(s.score), s.src, s.trg, s.cases, s.ctrls] for s in r.scores]
+            out["perm"] = np.asarray(r.permuted_scores, dtype=np.float64).tolist()  # repr round-trips doubles exactly
+        reply(out)
+
+
+class RefWorker:
+    def __init__(self, path, method, kind, threads, top_k):
+        env = dict(os.environ)
+        env.pop("GCRE_B200_LIB", None)
+        self.proc = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker", path, method, kind, str(threads), str(top_k)],
+                                     stdin=subprocess.PIPE, stdout=subprocess.PIPE, env=env, cwd=ROOT)
+        self.joins = 0
+        self.setup_s = self._read()["setup_s"]
+
+    def _read(self):
+        line = self.proc.stdout.readline()
+        if not line:
+            raise RuntimeError(f"reference worker died (exit code {self.proc.poll()})")
+        return json.loads(line)
+
+    def join(self, x, results=False):
+        self.proc.stdin.write((json.dumps({"x": int(x), "results": bool(results)}) + "\n").encode())
+        self.proc.stdin.flush()
+        self.joins += 1
+        return self._read()
+
+    def close(self):
+        if self.proc.poll() is None:
+            try:
+                self.proc.stdin.write(b'{"quit": true}\n')
+                self.proc.stdin.flush()
+                self.proc.stdin.close()
+                self.proc.wait(timeout=60)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+                self.proc.wait()
+
+
 class ReferenceArm:
     """The reference's own JoinExec::join (oracle/_ref: unmodified reference sources, g++ -O3 -march=<host level> -mpopcnt)
-    on all host cores.  setup() replays levels 1-3 once per method (untimed, like our arm's resident inputs); sample()
-    times the last-level join - the whole join when it fits the time budget, else a bounded prefix of upstream rows."""
+    on all host cores, in worker subprocesses.  Each worker replays levels 1-3 once (untimed, like our arm's resident
+    inputs); sample() times the last-level join - the whole join when it fits the time budget, else a bounded prefix of
+    upstream rows - and can return that join's results for the parity check against the GPU."""
 
     def __init__(self, w, a, methods=("method1", "method2")):
-        from geneticscre_b200 import schedule
-        from oracle import pyoracle as po
-
         if a.path_length < 4:
             raise RuntimeError("the CPU baseline times the level-4 join: needs path_length >= 4")
-        self.po, self.w, self.a, self.methods = po, w, a, methods
+        if w.value_table is None:
+            raise RuntimeError("the CPU baseline needs the value table on the host")
+        sys.path.insert(0, ROOT)
+        from oracle import pyoracle as po  # (availability / ISA level only; the joins run in the workers)
+
+        self.w, self.a, self.methods = w, a, methods
         self.kind = "reference" if po.ref_available() else "port"
+        self.variant = po.ref_variant()
         self.cores = (os.cpu_count() or 1) if self.kind == "reference" else 1
+        # method 2 of the reference needs (and leaks) one (n+1)^2 f64 table per worker thread and join: bound both by the RAM
+        table_bytes = (w.n_patients + 1) ** 2 * 8
+        budget = 0.4 * mem_available_bytes() - 2 * table_bytes
+        self.threads = {"method1": self.cores, "method2": int(max(1, min(self.cores, budget // table_bytes)))}
+        self.joins_per_worker = {"method1": REF_JOINS_PER_WORKER["method1"],
+                                 "method2": int(max(1, min(REF_JOINS_PER_WORKER["method2"], budget // (self.threads["method2"] * table_bytes))))}
         self.lv = w.net.levels["4"]
         self.csum = np.cumsum(self.lv.count.astype(np.int64))
-        self.state = {}
-        for method in methods:
-            if self.kind == "reference":
-                ex = po.RefExec(method, w.n_cases, w.n_ctrls, w.n_perms)
-                ex.nthreads = self.cores
-            else:
-                ex = po.OracleExec(method, w.n_cases, w.n_ctrls, w.n_perms)
-            ex.top_k = a.top_k
-            ex.setValueTable(w.value_table)
-            ex.setPermutedMasks(w.perm_masks)
-            t0 = time.time()
-            _, kept = schedule.replay_levels(ex, po.UidRelSet, w, 3, only=())
-            self.state[method] = dict(ex=ex, p0=kept["paths3"], p1=kept["paths2"], setup_s=time.time() - t0, plan=None)
+        self.path = workload_file(w, a)
+        self.workers, self.plan, self.setup_s = {}, {}, {}
 
-    def _run(self, st, x):
-        lv, po = self.lv, self.po
-        x = int(min(max(x, 1), lv.n_uids))
-        uids = po.UidRelSet(4, lv.src[:x], lv.trg[:x], lv.count[:x], lv.location[:x], lv.signs[:x])
-        sub = st["p0"] if x == lv.n_uids else st["p0"].select(np.arange(x, dtype=np.int32))
-        t = time.time()
-        st["ex"].join(uids, sub, st["p1"], st["ex"].createPathSet(0))
-        return time.time() - t, int(self.csum[x - 1])
+    def close(self):
+        for wk in self.workers.values():
+            wk.close()
+        self.workers = {}
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
 
-    def sample(self, target_s):
-        """One bounded sample per method; returns the cpu_baseline object."""
+    def _worker(self, method, need=1):
+        wk = self.workers.get(method)
+        if wk is not None and wk.joins + need > max(self.joins_per_worker[method], need):
+            wk.close()
+            wk = None
+        if wk is None:
+            wk = self.workers[method] = RefWorker(self.path, method, self.kind, self.threads[method], self.a.top_k)
+            self.setup_s[method] = wk.setup_s
+        return wk
+
+    def calibrate(self, method, target_s):
+        """two-point calibration: a join call has a fixed cost (per-thread state; for method 2 a per-thread clone of the
+        (n+1)^2 table, src/methods.h:128) plus a per-pair cost"""
+        lv = self.lv
+        wk = self._worker(method, need=2)
+        x1 = max(64, lv.n_uids // 400)
+        r1 = wk.join(x1)
+        r2 = wk.join(min(lv.n_uids, 4 * x1))
+        rate = max(r2["pairs"] - r1["pairs"], 1) / max(r2["seconds"] - r1["seconds"], 1e-6)
+        t_fixed = max(r1["seconds"] - r1["pairs"] / rate, 0.0)
+        if t_fixed + lv.n_pairs / rate <= 3.0 * target_s:
+            x = lv.n_uids
+        else:
+            x = int(np.searchsorted(self.csum, max(target_s - t_fixed, 0.25 * target_s) * rate)) + 1
+        self.plan[method] = (min(x, lv.n_uids), t_fixed)
+
+    def sample(self, target_s, results=False):
+        """One bounded sample per method; returns the cpu_baseline object (and, with `results`, each join's output)."""
         lv, w = self.lv, self.w
-        total_pp, total_t, detail = 0.0, 0.0, {}
+        total_pp, total_t, detail, outputs = 0.0, 0.0, {}, {}
         for method in self.methods:
-            st = self.state[method]
-            if st["plan"] is None:
-                # two-point calibration: a join call has a fixed cost (per-thread state; for method 2 a per-thread clone
-                # of the (n+1)^2 table, src/methods.h:128) plus a per-pair cost
-                x1 = max(64, lv.n_uids // 400)
-                t1, q1 = self._run(st, x1)
-                t2, q2 = self._run(st, min(lv.n_uids, 4 * x1))
-                rate = max(q2 - q1, 1) / max(t2 - t1, 1e-6)
-                t_fixed = max(t1 - q1 / rate, 0.0)
-                if t_fixed + lv.n_pairs / rate <= 3.0 * target_s:
-                    x = lv.n_uids
-                else:
-                    x = int(np.searchsorted(self.csum, max(target_s - t_fixed, 0.25 * target_s) * rate)) + 1
-                st["plan"] = (x, t_fixed)
-            x, t_fixed = st["plan"]
-            t_run, pairs_run = self._run(st, x)
-            total_pp += pairs_run * w.n_perms
-            total_t += t_run
-            detail[method] = {"pairs": pairs_run, "of_level4_pairs": lv.n_pairs, "seconds": round(t_run, 3),
-                              "pair_perm_per_s": pairs_run * w.n_perms / t_run, "fixed_s_per_join": round(t_fixed, 3),
-                              "setup_levels_1_3_s": round(st["setup_s"], 2)}
+            if method not in self.plan:
+                self.calibrate(method, target_s)
+            x, t_fixed = self.plan[method]
+            r = self._worker(method).join(x, results=results)
+            # a join's fixed cost (thread start-up; method 2: every thread's private copy of the (n+1)^2 table) is paid once per
+            # join whatever its size: a prefix sample is charged its share of it, so the figure estimates the WHOLE join's rate
+            share = r["pairs"] / max(lv.n_pairs, 1)
+            fixed = min(t_fixed, 0.9 * r["seconds"])
+            t_eff = r["seconds"] - fixed * (1.0 - share)
+            total_pp += r["pairs"] * w.n_perms
+            total_t += t_eff
+            detail[method] = {"pairs": r["pairs"], "of_level4_pairs": lv.n_pairs, "upstream_rows": r["x"], "seconds_measured": round(r["seconds"], 3),
+                              "seconds_charged": round(t_eff, 3), "pair_perm_per_s": r["pairs"] * w.n_perms / t_eff,
+                              "fixed_s_per_join": round(t_fixed, 3), "threads": self.threads[method],
+                              "setup_levels_1_3_s": round(self.setup_s[method], 2)}
+            if results:
+                outputs[method] = r
         compiler = ""
         try:
             compiler = open(os.path.join(ROOT, "oracle", "_ref", "COMPILER.txt")).read().strip()
         except OSError:
             pass
-        how = (f"reference built with {compiler} -O3 -march={self.po.ref_variant()} -mpopcnt" if self.kind == "reference"
+        how = (f"reference built with {compiler} -O3 -march={self.variant} -mpopcnt" if self.kind == "reference"
                else "scalar C restatement (oracle/gcre_oracle.c), the reference build is absent")
-        return {"value": total_pp / total_t, "unit": "pair*perm/s", "cores": self.cores, "kind": self.kind,
-                "sample": f"level-4 join (paths3 x paths2) per method ({'+'.join(self.methods)}): the whole join when it fits ~{3 * target_s:.0f} s, "
-                          f"else the first upstream rows sized for ~{target_s:.0f} s; {w.n_perms} perms, W64={(w.n_patients + 63) // 64}; {how}; "
-                          f"nthreads={self.cores}", "seconds": round(total_t, 3), "detail": detail}
+        out = {"value": total_pp / total_t, "unit": "pair*perm/s", "cores": self.cores, "kind": self.kind,
+               "sample": f"level-4 join (paths3 x paths2) per method ({'+'.join(self.methods)}): the whole join when it fits ~{3 * target_s:.0f} s, "
+                         f"else the first upstream rows sized for ~{target_s:.0f} s; {w.n_perms} perms, W64={(w.n_patients + 63) // 64}; {how}; "
+                         f"nthreads={self.threads['method1']} (method 2: {self.threads['method2']}); a prefix sample is charged its pro-rata share of the "
+                         f"join's fixed cost (method 2 copies the (n+1)^2 table once per thread and join); run in worker subprocesses replaced every "
+                         f"{self.joins_per_worker['method2']} method-2 joins (the reference never frees those copies)",
+               "seconds": round(total_t, 3), "detail": detail}
+        return (out, outputs) if results else out
 
 
 def run_reference_arm(a):
@@ -233,18 +390,25 @@ def run_reference_arm(a):
     t0 = time.time()
     w, _ = make_workload(a)
     arm = ReferenceArm(w, a)
-    per_method_s = max(1.0, min(a.cpu_seconds, 90.0 / max(a.steps + a.warmup, 1) / 2))
-    vals = []
-    for i in range(a.warmup + a.steps):
-        r = arm.sample(per_method_s)
-        if i >= a.warmup:
-            vals.append(r)
+    try:
+        # K + W bounded samples inside ~3 minutes: per-sample join time per method, on top of ~3 s of worker set-up per
+        # method-2 worker (value table, masks, levels 1-3)
+        per_method_s = max(1.0, min(a.cpu_seconds, 90.0 / max(a.steps + a.warmup, 1) / 2))
+        vals = []
+        for i in range(a.warmup + a.steps):
+            r = arm.sample(per_method_s)
+            if i >= a.warmup:
+                vals.append(r)
+            sys.stderr.write(f"[bench] reference step {i}: {r['value']:.4g} pair*perm/s in {r['seconds']:.2f} s\n")
+    finally:
+        arm.close()
     value = float(np.mean([v["value"] for v in vals])) if vals else 0.0
     last = vals[-1] if vals else {"cores": arm.cores, "kind": arm.kind, "sample": ""}
     ms = 1e3 * float(np.mean([v["seconds"] for v in vals])) if vals else None
+    cfg = full_config(a, w, max(a.gpus, 1))
     line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "impl": "reference", "config": workload_config(a, w),
+            "data": "synthetic", "impl": "reference", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "pair*perm/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": value, "unit": "pair*perm/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": round(time.time() - t0, 1)}
@@ -278,7 +442,52 @@ def emit_line(line):
         os.write(_REAL_STDOUT, data)
 
 
+def check_parity(ref_out, last_out, state, lv4, w, api):
+    """GPU level-4 results against the reference's on the same inputs -> the `parity` object of the line (raises on mismatch).
+
+    When the reference ran the whole join, the result of the last TIMED step is compared; when it ran a prefix of the upstream
+    rows (bounded sample), the GPU re-runs exactly that prefix (uid_range) on its resident operands."""
+    from oracle import pyoracle as po  # the checker
+
+    out = {"checked": True, "rule": "SURVEY App. A.7: f32 permutation maxima bit-exact, top-K score multiset bit-exact, entries above the K-th score identical",
+           "against": "the reference's own join (oracle/_ref) in the cpu_baseline leg of this run", "level4_pairs": 0, "mismatches": 0, "methods": {}}
+    for method, r in ref_out.items():
+        want = po.JoinedRes([po.Score(float(s[0]), int(s[1]), int(s[2]), int(s[3]), int(s[4])) for s in r["scores"]], np.asarray(r["perm"], dtype=np.float64))
+        x = int(r["x"])
+        if x == lv4.n_uids and "4" in last_out[method][1]:
+            got, how = last_out[method][1]["4"], "whole join, result of the last timed step"
+        else:
+            got, how = rerun_level4_prefix(state[method], lv4, w, x, api), f"first {x} upstream rows, re-run on the GPU with uid_range"
+        try:
+            po.compare_results(got, want, what=f"bench parity {method}")
+            bad = 0
+        except AssertionError as e:
+            sys.stderr.write(f"[bench] PARITY MISMATCH {method}: {e}\n")
+            bad = 1
+        out["methods"][method] = {"pairs": int(r["pairs"]), "compared": how, "perm_maxima": int(want.permuted_scores.shape[0]), "top_k": len(want.scores), "mismatch": bad}
+        out["level4_pairs"] += int(r["pairs"])
+        out["mismatches"] += bad
+    if out["mismatches"]:
+        raise AssertionError(f"GPU results differ from the reference's on the benchmarked workload: {out}")
+    return out
+
+
+def rerun_level4_prefix(st, lv4, w, x, api):
+    """Levels 1-3 again (resident inputs) and the level-4 join over the first x upstream rows."""
+    ex, d1, d2 = st["ex"], st["d1"], st["d2"]
+    lv = w.net.levels
+    p1 = ex.createPathSet(lv["1a"].n_pairs)
+    ex.join(st["uid"]["1a"], ex.createPathSet(lv["1a"].n_uids), d1.select(w.net.data_idx["1a"]), p1)
+    p2 = ex.createPathSet(lv["2"].n_pairs)
+    ex.join(st["uid"]["2"], p1, d1.select(w.net.data_idx["2"]), p2)
+    p3 = ex.createPathSet(lv["3"].n_pairs)
+    ex.join(st["uid"]["3"], p2, d1.select(w.net.data_idx["3"]), p3)
+    return ex.join(st["uid"]["4"], p3, p2, ex.createPathSet(0), uid_range=(0, x))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--ref-worker":
+        return ref_worker_main(sys.argv[2], sys.argv[3], sys.argv[4], int(sys.argv[5]), int(sys.argv[6]))
     a = parse_args()
     claim_stdout()
     if a.impl == "reference":
@@ -357,8 +566,9 @@ def main():
             _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_all"].data_ptr() + 4 * ex.iterations * rank, ex.iterations))
             dist.all_reduce(st["perm_all"], op=dist.ReduceOp.MAX)
 
-    def schedule_resident(st, results, collective=True):
-        """Levels 1a,1b,2,3,(4,5) with device-resident inputs; the last level is sharded across ranks."""
+    def schedule_resident(st, results, collective=True, single=False):
+        """Levels 1a,1b,2,3,(4,5) with device-resident inputs; the last level is sharded across ranks
+        (`single`: this rank alone does the whole job - the cross-check of the multi-GPU result)."""
         ex, d1, d2, uid = st["ex"], st["d1"], st["d2"], st["uid"]
         zero = ex.createPathSet(0)
         info = {}
@@ -375,11 +585,11 @@ def main():
             else:
                 operand = results["_p3"]
             res_set = ex.createPathSet(lv[k].n_pairs) if (keep or (k in ("2", "3") and a.path_length > int(k))) else zero
-            if k == last and shard_perms:
+            if k == last and shard_perms and not single:
                 r = ex.join(uid[k], prev, operand, res_set)
                 if collective:
                     merge_last_level(st, results)
-            elif k == last and world > 1:
+            elif k == last and world > 1 and not single:
                 r = ex.join(uid[k], prev, operand, zero, uid_range=my_shard, skip_host_perm=True)
                 _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations))
                 # ONE data-path collective per join: NCCL allreduce(max) of the f32 maxima (+ a K-entry gather)
@@ -454,6 +664,47 @@ def main():
     ms_step = float(t_ms.item()) / a.steps
     pp_step = pairs_per_step(w, a.path_length) * w.n_perms * (world if shard_perms else 1)  # whole job, all ranks
     value = pp_step / (ms_step * 1e-3)
+
+    # ---- N > 1: the merged result against a single-rank recomputation (after the timed region) ----
+    multi_parity = None
+    if world > 1 and last_out is not None:
+        bad = 0
+        for method in ("method1", "method2"):
+            st = state[method]
+            ex = st["ex"]
+            merged = last_out[method][1][last]
+            if shard_perms:
+                # rank r recomputes, alone, the block of permutations rank (r + 1) % N scored, and compares it bit for bit with
+                # that block of the all-reduced N x I vector; the top-K (permutation independent) must be the same on every rank
+                blk = (rank + 1) % world
+                all_red = st["perm_all"].cpu().numpy().astype(np.float64)
+                ex.setPermutedMasks(synth.make_perm_masks(w.n_cases, w.n_ctrls, w.n_perms, a.seed + 3 + 1000 * blk))
+                res = {}
+                schedule_resident(st, res, collective=False, single=True)
+                mine = res[last]
+                bad += int(not np.array_equal(mine.permuted_scores.view(np.uint64), all_red[blk * ex.iterations: blk * ex.iterations + w.n_perms].view(np.uint64)))
+                bad += int([(s_.score, s_.src, s_.trg, s_.cases, s_.ctrls) for s_ in mine.scores] != [(s_.score, s_.src, s_.trg, s_.cases, s_.ctrls) for s_ in merged.scores])
+                ex.setPermutedMasks(w.perm_masks)
+                del res
+            else:
+                # every rank recomputes the whole last-level join and compares it with the merged shards
+                res = {}
+                schedule_resident(st, res, single=True)
+                mine = res[last]
+                bad += int(not np.array_equal(mine.permuted_scores.view(np.uint64), np.asarray(merged.permuted_scores, dtype=np.float64).view(np.uint64)))
+                bad += int([(s_.score, s_.src, s_.trg, s_.cases, s_.ctrls) for s_ in mine.scores] != [(s_.score, s_.src, s_.trg, s_.cases, s_.ctrls) for s_ in merged.scores])
+                del res
+            tops = [None] * world
+            dist.all_gather_object(tops, [(s_.score, s_.src, s_.trg, s_.cases, s_.ctrls) for s_ in merged.scores])
+            bad += int(any(t_ != tops[0] for t_ in tops))
+        t_bad = torch.tensor([bad], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t_bad, op=dist.ReduceOp.SUM)
+        multi_parity = {"checked": True, "mismatches": int(t_bad.item()),
+                        "what": ("every rank recomputed, alone, the permutation block of its neighbour and compared it bit for bit with that block of the "
+                                 "all-reduced maxima; top-K identical on all ranks" if shard_perms else
+                                 "every rank recomputed the whole last-level join alone and compared maxima (bit for bit) and top-K with the merged shards")}
+        if multi_parity["mismatches"]:
+            raise AssertionError(f"multi-GPU result differs from the single-rank recomputation: {multi_parity}")
 
     # ---- roofline of the dominant kernel: the last-level join of each method, timed live by CUDA events inside join ----
     roof = None
@@ -655,25 +906,32 @@ def main():
                 ex.close()
             d2h_holder[0] = d2h
 
-        step_e2e()
+        for _ in range(2):  # untimed: block cache, page-locked staging and the copy streams reach their steady state
+            step_e2e()
         sync_all()
         gc.collect()
         gc.freeze()
         gc.disable()  # as in the resident region: a cyclic GC pass costs 100+ ms with torch imported
-        t0 = time.perf_counter()
-        e2e_steps = max(1, min(a.steps, 3))
+        e2e_steps = max(10, a.steps) if a.e2e_steps <= 0 else a.e2e_steps
+        per_step = []
         for i in range(e2e_steps):
+            sync_all()  # every rank starts the step together; the step's own time is host wall clock, result read-back included
             t_dbg = time.perf_counter()
             step_e2e()
-            if dbg:
-                sys.stderr.write(f"[bench] rank {rank} e2e step {i}: {(time.perf_counter() - t_dbg) * 1e3:.1f} ms\n")
-        sync_all()
-        dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            per_step.append(time.perf_counter() - t_dbg)
         gc.enable()
+        t_steps = torch.tensor(per_step, dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_steps, op=dist.ReduceOp.MAX)  # per step: the slowest rank
+        per_step = t_steps.cpu().numpy()
+        if rank == 0:
+            sys.stderr.write("[bench] e2e ms per step (max over ranks): " + " ".join(f"{1e3 * t:.1f}" for t in per_step) + "\n")
+        dt = torch.tensor([float(per_step.mean())], dtype=torch.float64)
         e2e = {"value": pp_step / float(dt.item()), "unit": "pair*perm/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_holder[0]),
-               "ms_per_step": float(dt.item()) * 1e3, "steps": e2e_steps, "host_input_bytes_per_step": int(host_input_bytes),
+               "ms_per_step": float(dt.item()) * 1e3, "steps": e2e_steps, "ms_per_step_median": float(np.median(per_step)) * 1e3,
+               "ms_per_step_max": float(per_step.max()) * 1e3, "ms_per_step_min": float(per_step.min()) * 1e3,
+               "timing": "host wall clock per step incl. uploads and result read-back, max over ranks per step; value = pair*perm per step / MEAN step time", "host_input_bytes_per_step": int(host_input_bytes),
                "input_path": ("rank 0 packs the int matrices on host threads and uploads bits + table once per step, NCCL broadcast to the other ranks; "
                               "every rank uploads its own permutation block" if fanout else
                               "int matrices packed to bits by host threads inside gcre_pathset_load_i32, bits uploaded" if host_packed else
@@ -684,23 +942,30 @@ def main():
                        if overlap else
                        "host IntegerMatrix data + CaseORControl int matrix + f64 value table + join indices uploaded every step (pinned), per method"}
 
-    cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline and w.value_table is not None:
+    # ---- CPU baseline + parity of what was benchmarked: the reference's own level-4 join on the bench inputs, compared with
+    #      the GPU's level-4 result of the last timed step (SURVEY App. A.7 rule: f32 maxima bit for bit, the multiset of top-K
+    #      scores, every entry above the K-th score; entries tied with the K-th score only need to carry that score) ----
+    cpu, parity = None, None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and w.value_table is not None and a.path_length >= 4:
+        arm = None
         try:
-            cpu = ReferenceArm(w, a).sample(a.cpu_seconds)
+            arm = ReferenceArm(w, a)
+            cpu, ref_out = arm.sample(a.cpu_seconds, results=True)
+            parity = check_parity(ref_out, last_out, state, lv["4"], w, api)
+        except AssertionError:
+            raise
         except Exception as e:  # the GPU numbers stand on their own
             cpu = {"value": None, "unit": "pair*perm/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}
+        finally:
+            if arm is not None:
+                arm.close()
 
     if rank == 0:
-        cfg = workload_config(a, w)
-        cfg["permutations_total"] = w.n_perms * (world if shard_perms else 1)
-        cfg["parallelism"] = ("1 GPU" if world == 1 else
-                              f"{world} GPUs, one block of {w.n_perms} permutations per GPU over all pairs; maxima merged with one NCCL allreduce(max)" if shard_perms else
-                              f"{world} GPUs, level-{last} upstream rows sharded by pair count; one NCCL allreduce(max) per join + top-K gather")
+        cfg = full_config(a, w, world)
         line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (shard_perms or world == 1) else "strong", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,
-                "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu, "per_level": per_level,
+                "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "multi_gpu_parity": multi_parity, "per_level": per_level,
                 "pair_perm_per_step": pp_step, "workload_gen_s": round(gen_s, 1)}
         emit_line(line)
     if world > 1:

@@ -82,7 +82,7 @@ class UidRelSet:
 
     def release(self):
         r, self._resident = getattr(self, "_resident", None), None
-        if r is not None and r[0]._h:
+        if r is not None:  # legal after the exec is gone: gcre_exec_destroy orphans its children
             r[0]._lib.gcre_uidset_destroy(r[1])
 
     def __del__(self):
@@ -103,7 +103,7 @@ class PathSet:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h and self.ex._h:
+        if h:  # legal after the exec is gone: gcre_exec_destroy orphans its children
             self.ex._lib.gcre_pathset_destroy(h)
 
     def load(self, data):

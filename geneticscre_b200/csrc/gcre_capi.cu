@@ -13,6 +13,7 @@
 #include <limits>
 #include <map>
 #include <mutex>
+#include <set>
 #include <unordered_map>
 #include <new>
 #include <string>
@@ -150,6 +151,19 @@ struct BlockCache {
     cudaEventRecord(b.ev, stream);
     free_blocks.emplace(b.cap, b);
   }
+  // give idle blocks back to the driver, largest first, until at most `limit` bytes stay cached
+  void trim(size_t limit) {
+    size_t idle = 0;
+    for (auto& kv : free_blocks) idle += kv.second.cap;
+    while (idle > limit && !free_blocks.empty()) {
+      auto it = std::prev(free_blocks.end());
+      if (it->second.ev) cudaEventSynchronize(it->second.ev);
+      cudaFree(it->second.p);
+      cudaEventDestroy(it->second.ev);
+      idle -= it->second.cap;
+      free_blocks.erase(it);
+    }
+  }
   void release_all() {
     for (auto& kv : free_blocks) {
       cudaFree(kv.second.p);
@@ -162,9 +176,20 @@ struct BlockCache {
 static std::mutex g_cache_mu;
 static std::map<int, BlockCache> g_cache;  // per device
 
+static size_t cache_limit_bytes() {
+  if (const char* e = std::getenv("GCRE_CACHE_MAX_MB")) return (size_t)std::strtoull(e, nullptr, 10) << 20;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+    cudaGetLastError();
+    return (size_t)64 << 30;
+  }
+  return total_b / 2;
+}
+
 static cudaError_t dev_alloc(const gcre_exec* ex, void** out, size_t bytes);
 static void dev_free(const gcre_exec* ex, void* p);
 static void reap_staged(gcre_exec* ex, bool all);
+static void free_uidset_buffers(struct gcre_uidset* us);
 
 struct DevBuf {  // grow-only device scratch owned by one exec
   const gcre_exec* owner = nullptr;
@@ -281,6 +306,9 @@ static void unpool_event(int device, bool timing, cudaEvent_t ev) {
   (timing ? g_pools.timing_events : g_pools.plain_events)[device].push_back(ev);
 }
 
+struct gcre_pathset;
+struct gcre_uidset;
+
 struct gcre_exec {
   int M = 1, n_cases = 0, n_ctrls = 0, n = 0, W64 = 0, Wp = 0, iters = 0, Ip = 0, Iw = 0, device = 0, sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -314,6 +342,11 @@ struct gcre_exec {
   unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total, [2..3] 64-bit work counter of the sparse kernel
   DevBuf cand, scratch, scan_tmp;
   unsigned* h_scalars = nullptr;  // pinned
+  // path sets and join indices created from this exec: gcre_exec_destroy frees their device memory and orphans them (ex =
+  // nullptr), so destroying the exec first is legal and a later gcre_pathset_destroy only deletes the host object
+  mutable std::mutex child_mu;
+  mutable std::set<gcre_pathset*> pathsets;
+  mutable std::set<gcre_uidset*> uidsets;
 };
 
 struct gcre_pathset {
@@ -486,6 +519,22 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   if (ex->own_stream) cudaStreamSynchronize(ex->own_stream);
   if (ex->copy_stream) cudaStreamSynchronize(ex->copy_stream);
   reap_staged(ex, true);
+  {
+    // children outlive the exec as empty shells: their device memory goes back to the cache now
+    std::lock_guard<std::mutex> lock(ex->child_mu);
+    for (gcre_pathset* ps : ex->pathsets) {
+      dev_free(ex, ps->d_rows);
+      ps->d_rows = nullptr;
+      drop_view(ps);
+      ps->ex = nullptr;
+    }
+    for (gcre_uidset* us : ex->uidsets) {
+      free_uidset_buffers(us);
+      us->ex = nullptr;
+    }
+    ex->pathsets.clear();
+    ex->uidsets.clear();
+  }
   for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
                   (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk})
     dev_free(ex, p);
@@ -502,6 +551,12 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   unpool_event(ex->device, false, ex->ev_order);
   unpool_stream(ex->device, ex->copy_stream);
   unpool_stream(ex->device, ex->own_stream);
+  {
+    // keep the cache from starving other allocators of the process (torch, NCCL): above GCRE_CACHE_MAX_MB of idle blocks
+    // (default: half of the device memory) the largest ones go back to the driver
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    g_cache[ex->device].trim(cache_limit_bytes());
+  }
   delete ex;
   return GCRE_OK;
 }
@@ -760,6 +815,9 @@ extern "C" int gcre_exec_set_permuted_masks_u64(gcre_exec* ex, const uint64_t* m
 // ------------------------------------------------------------------------------------------------------------------
 static inline size_t row_words(const gcre_exec* ex) { return (size_t)ex->Wp * ex->M; }
 
+// clear bits at patient indices >= n in rows [row0, row0 + rows) (packed inputs / raw row writes may carry them)
+static int mask_tail(const gcre_exec* ex, gcre_pathset* ps, uint32_t row0, uint32_t rows);
+
 extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_pathset** out) {
   if (!ex || !out) return fail(GCRE_ERR_ARG, "null argument");
   *out = nullptr;
@@ -777,16 +835,40 @@ extern "C" int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_path
     }
     ps->zero_pending = true;
   }
+  {
+    std::lock_guard<std::mutex> lock(ex->child_mu);
+    ex->pathsets.insert(ps);
+  }
   *out = ps;
   return GCRE_OK;
 }
 
 extern "C" int gcre_pathset_destroy(gcre_pathset* ps) {
   if (!ps) return GCRE_OK;
-  cudaSetDevice(ps->ex->device);
-  dev_free(ps->ex, ps->d_rows);  // back to the block cache, no driver call
-  drop_view(ps);
+  if (ps->ex) {  // (an orphan's device memory went back to the cache when its exec was destroyed)
+    cudaSetDevice(ps->ex->device);
+    {
+      std::lock_guard<std::mutex> lock(ps->ex->child_mu);
+      ps->ex->pathsets.erase(ps);
+    }
+    dev_free(ps->ex, ps->d_rows);  // back to the block cache, no driver call
+    drop_view(ps);
+  }
   delete ps;
+  return GCRE_OK;
+}
+
+#define LIVE(obj)                                                                                  \
+  do {                                                                                             \
+    if (!(obj)->ex) return fail(GCRE_ERR_ARG, "the JoinExec this object belongs to was destroyed"); \
+  } while (0)
+
+static int mask_tail(const gcre_exec* ex, gcre_pathset* ps, uint32_t row0, uint32_t rows) {
+  if (!rows || ((ex->n & 63) == 0 && ex->Wp == ex->W64)) return GCRE_OK;
+  const long long halves = (long long)rows * ex->M;
+  mask_tail_kernel<<<grid_for(halves, 256), 256, 0, ex->stream>>>(ps->d_rows + (size_t)row0 * row_words(ex), halves, ex->Wp, ex->W64, ex->n);
+  CK(cudaGetLastError());
+  LAUNCHED();
   return GCRE_OK;
 }
 
@@ -819,13 +901,16 @@ static int pathset_max_half_pop(gcre_pathset* ps, long long* out) {
 
 extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint32_t rows, int cols) {
   if (!ps || (!data && rows > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  LIVE(ps);
   gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
   CKS(use_device(ex));
   // src/gcre_paths.h:60: check_true(size == data.size())
   if (rows != ps->size) return fail(GCRE_ERR_ASSERT, "assertion");
-  // src/gcre_paths.h:63: check_index(data[r].size(), width_ul * 64); our rows hold W64*64 patients, and a column count
-  // equal to n is always accepted (the reference throws when n is a multiple of its SIMD width: SURVEY App. D1)
-  if (rows > 0 && (cols < 0 || cols > ex->W64 * 64)) return fail(GCRE_ERR_RANGE, "assertion");
+  // src/gcre_paths.h:63: check_index(data[r].size(), width_ul * 64); a column count equal to n is always accepted (the
+  // reference throws when n is a multiple of its SIMD width: SURVEY App. D1)
+  // Columns beyond the n = num_cases + num_ctrls patients are rejected (the reference would accept up to its SIMD-padded
+  // width and count such bits as controls of the true score only - there is no patient they could belong to).
+  if (rows > 0 && (cols < 0 || cols > ex->n)) return fail(GCRE_ERR_RANGE, "assertion");
   if (rows == 0) return GCRE_OK;
   ps->zero_pending = false;
   CK(cudaMemsetAsync(ps->d_rows, 0, (size_t)ps->size * row_words(ex) * 8, ex->stream));
@@ -880,6 +965,7 @@ extern "C" int gcre_pathset_load_i32(gcre_pathset* ps, const int32_t* data, uint
 // of this exec synchronises it).
 extern "C" int gcre_pathset_load_bits_device(gcre_pathset* ps, const uint64_t* d_bits, uint32_t rows, int words_per_row) {
   if (!ps || (!d_bits && rows > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  LIVE(ps);
   gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
   CKS(use_device(ex));
   if (rows != ps->size) return fail(GCRE_ERR_ASSERT, "assertion");
@@ -892,6 +978,7 @@ extern "C" int gcre_pathset_load_bits_device(gcre_pathset* ps, const uint64_t* d
                                                                                              (int)row_words(ex));
     CK(cudaGetLastError());
     LAUNCHED();
+    if (words_per_row == ex->W64) CKS(mask_tail(ex, ps, 0, rows));
   }
   ps->max_half_pop = -1;
   drop_view(ps);
@@ -923,6 +1010,7 @@ extern "C" int gcre_host_pack_i32(const int32_t* data, uint32_t rows, int cols, 
 
 extern "C" int gcre_pathset_load_bits(gcre_pathset* ps, const uint64_t* bits, uint32_t rows, int words_per_row) {
   if (!ps || (!bits && rows > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  LIVE(ps);
   gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
   CKS(use_device(ex));
   if (rows != ps->size) return fail(GCRE_ERR_ASSERT, "assertion");
@@ -938,6 +1026,7 @@ extern "C" int gcre_pathset_load_bits(gcre_pathset* ps, const uint64_t* bits, ui
                                                                                              words_per_row, ps->d_rows, (int)row_words(ex));
     CK(cudaGetLastError());
       LAUNCHED();
+    if (words_per_row == ex->W64) CKS(mask_tail(ex, ps, 0, rows));
     CK(cudaStreamSynchronize(ex->stream));
   }
   ps->max_half_pop = -1;
@@ -947,6 +1036,7 @@ extern "C" int gcre_pathset_load_bits(gcre_pathset* ps, const uint64_t* bits, ui
 
 extern "C" int gcre_pathset_select(const gcre_pathset* ps, const int32_t* indices, uint32_t n, gcre_pathset** out) {
   if (!ps || !out || (!indices && n > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  LIVE(ps);
   *out = nullptr;
   gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
   CKS(use_device(ex));
@@ -987,6 +1077,7 @@ extern "C" int gcre_pathset_select(const gcre_pathset* ps, const int32_t* indice
 
 extern "C" int gcre_pathset_set_row(gcre_pathset* ps, uint32_t idx, const uint64_t* words) {
   if (!ps || !words) return fail(GCRE_ERR_ARG, "null argument");
+  LIVE(ps);
   gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
   CKS(use_device(ex));
   if (idx >= ps->size) return fail(GCRE_ERR_RANGE, "assertion");  // src/gcre_paths.h:50
@@ -994,6 +1085,7 @@ extern "C" int gcre_pathset_set_row(gcre_pathset* ps, uint32_t idx, const uint64
   for (int h = 0; h < ex->M; h++)
     CK(cudaMemcpyAsync(ps->d_rows + (size_t)idx * row_words(ex) + (size_t)h * ex->Wp, words + (size_t)h * ex->W64, (size_t)ex->W64 * 8,
                        cudaMemcpyHostToDevice, ex->stream));
+  CKS(mask_tail(ex, ps, idx, 1));
   CK(cudaStreamSynchronize(ex->stream));
   ps->max_half_pop = -1;
   drop_view(ps);
@@ -1002,6 +1094,7 @@ extern "C" int gcre_pathset_set_row(gcre_pathset* ps, uint32_t idx, const uint64
 
 extern "C" int gcre_pathset_get_row(const gcre_pathset* ps, uint32_t idx, uint64_t* words) {
   if (!ps || !words) return fail(GCRE_ERR_ARG, "null argument");
+  LIVE(ps);
   const gcre_exec* ex = ps->ex;
   CKS(use_device(ex));
   if (idx >= ps->size) return fail(GCRE_ERR_RANGE, "assertion");  // src/gcre_paths.h:45
@@ -1015,6 +1108,7 @@ extern "C" int gcre_pathset_get_row(const gcre_pathset* ps, uint32_t idx, uint64
 
 extern "C" int gcre_pathset_download(const gcre_pathset* ps, uint64_t* out) {
   if (!ps || (!out && ps->size)) return fail(GCRE_ERR_ARG, "null argument");
+  LIVE(ps);
   gcre_exec* ex = const_cast<gcre_exec*>(ps->ex);
   CKS(use_device(ex));
   if (!ps->size) return GCRE_OK;
@@ -1053,9 +1147,18 @@ static int ensure_diag(gcre_exec* ex, long long t_needed) {
   ex->d_diagDM = nullptr;
   ex->diag_cap = -1;
   const size_t entries = (size_t)(cap + 1) * (size_t)(cap + 2) / 2;
-  CK(dev_alloc(ex, (void**)&ex->d_diagD, entries * 8));
-  if (ex->M == 1) CK(dev_alloc(ex, (void**)&ex->d_diagF, entries * 4));
-  else CK(dev_alloc(ex, (void**)&ex->d_diagDM, entries * 8));
+  {
+    // (cap+1)(cap+2)/2 entries of 12 (method 1) or 16 (method 2) bytes: 26-34 GB at 65,535 carriers per half-row
+    cudaError_t e = dev_alloc(ex, (void**)&ex->d_diagD, entries * 8);
+    if (e == cudaSuccess) e = (ex->M == 1) ? dev_alloc(ex, (void**)&ex->d_diagF, entries * 4) : dev_alloc(ex, (void**)&ex->d_diagDM, entries * 8);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      dev_free(ex, ex->d_diagD);
+      ex->d_diagD = nullptr;
+      return fail(GCRE_ERR_NOMEM, "anti-diagonal value tables for joined rows of up to %lld carriers need %zu bytes of device memory (%s); "
+                  "the limit is set by the densest operand rows", t_needed, entries * (ex->M == 1 ? 12 : 16), cudaGetErrorString(e));
+    }
+  }
   build_diag_kernel<<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_vt, ex->vt_rows, ex->vt_cols, (unsigned)cap, ex->d_diagD, ex->d_diagF, ex->d_diagDM);
   CK(cudaGetLastError());
       LAUNCHED();
@@ -1126,30 +1229,39 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
     ps->view.pcnt_gen = gen;
   }
   const long long items = (long long)ps->size * ex->M;
-  CK(dev_alloc(ex, (void**)&ps->view.off, (size_t)(items + 1) * 4));
+  CK(dev_alloc(ex, (void**)&ps->view.off, (size_t)(items + 1) * 8));
   CK(dev_alloc(ex, (void**)&ps->view.len, std::max<size_t>(items, 1) * 4));
   CK(dev_alloc(ex, (void**)&ps->view.ncase, std::max<size_t>(items, 1) * 4));
-  CK(cudaMemsetAsync(ps->view.off, 0, (size_t)(items + 1) * 4, ex->stream));
-  uint32_t total = 0;
+  CK(cudaMemsetAsync(ps->view.off, 0, (size_t)(items + 1) * 8, ex->stream));
+  unsigned long long total = 0;
   if (items > 0) {
-    // true counts + padded counts -> exclusive offsets (cub scan over items + 1 entries, the last input is 0)
-    CKS(ex->scratch.ensure((size_t)(items + 1) * 4));
-    uint32_t* padded = (uint32_t*)ex->scratch.p;
-    CK(cudaMemsetAsync(padded, 0, (size_t)(items + 1) * 4, ex->stream));
+    // true counts + padded counts -> exclusive offsets (cub scan over items + 1 entries, the last input is 0).  Offsets are
+    // 64-bit: the carriers of a large kept set do not fit 32 bits (a 32-bit scan wrapped silently).
+    CKS(ex->scratch.ensure((size_t)(items + 1) * 8));
+    unsigned long long* padded = (unsigned long long*)ex->scratch.p;
+    CK(cudaMemsetAsync(padded, 0, (size_t)(items + 1) * 8, ex->stream));
     half_popcount_kernel<<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ps->view.len, padded);
     CK(cudaGetLastError());
     LAUNCHED();
     size_t tmp_bytes = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, padded, ps->view.off, (int)(items + 1), ex->stream));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, padded, ps->view.off, (long long)(items + 1), ex->stream));
     CKS(ex->scan_tmp.ensure(tmp_bytes));
-    CK(cub::DeviceScan::ExclusiveSum(ex->scan_tmp.p, tmp_bytes, padded, ps->view.off, (int)(items + 1), ex->stream));
+    CK(cub::DeviceScan::ExclusiveSum(ex->scan_tmp.p, tmp_bytes, padded, ps->view.off, (long long)(items + 1), ex->stream));
     LAUNCHED();
-    CK(cudaMemcpyAsync(&total, ps->view.off + items, 4, cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaMemcpyAsync(&total, ps->view.off + items, 8, cudaMemcpyDeviceToHost, ex->stream));
     CK(cudaStreamSynchronize(ex->stream));
   }
-  ps->view.total = total;
+  ps->view.total = (size_t)total;
   const bool wide = sparse_wide(ex->n);
-  CK(dev_alloc(ex, (void**)&ps->view.car, std::max<size_t>(total, 8) * (wide ? 4 : 2)));
+  {
+    const size_t car_bytes = std::max<size_t>((size_t)total, 8) * (wide ? 4 : 2);
+    cudaError_t e = dev_alloc(ex, (void**)&ps->view.car, car_bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      drop_view(ps);
+      return fail(GCRE_ERR_NOMEM, "carrier lists of a %u-row path set need %zu bytes of device memory: %s", ps->size, car_bytes, cudaGetErrorString(e));
+    }
+  }
   if (items > 0) {
     if (wide)
       build_lists_kernel<uint32_t><<<grid_for(items * 32, 256), 256, 0, ex->stream>>>(ps->d_rows, items, ex->Wp, ex->n_cases, ex->n, ps->view.off,
@@ -1311,15 +1423,25 @@ extern "C" int gcre_uidset_create(gcre_exec* ex, int path_length, const gcre_uid
     delete us;
     return rc;
   }
+  {
+    std::lock_guard<std::mutex> lock(ex->child_mu);
+    ex->uidsets.insert(us);
+  }
   *out = us;
   return GCRE_OK;
 }
 
 extern "C" int gcre_uidset_destroy(gcre_uidset* us) {
   if (!us) return GCRE_OK;
-  cudaSetDevice(us->ex->device);
-  cudaStreamSynchronize(us->ex->stream);
-  free_uidset_buffers(us);
+  if (us->ex) {
+    cudaSetDevice(us->ex->device);
+    cudaStreamSynchronize(us->ex->stream);
+    {
+      std::lock_guard<std::mutex> lock(us->ex->child_mu);
+      us->ex->uidsets.erase(us);
+    }
+    free_uidset_buffers(us);
+  }
   delete us;
   return GCRE_OK;
 }
@@ -1332,6 +1454,7 @@ extern "C" int gcre_join(gcre_exec* ex, int path_length, const gcre_uid_ref* uid
                          int* n_scores, double* out_perm, gcre_join_opts* opts) {
   if (!ex || !paths0 || !paths1 || !out_scores || !n_scores || (!uids && n_uids) || (!signs && n_signs))
     return fail(GCRE_ERR_ARG, "null argument");
+  if (paths0->ex != ex || paths1->ex != ex || (paths_res && paths_res->ex != ex)) return fail(GCRE_ERR_ARG, "path set belongs to another exec");
   CKS(use_device(ex));
   PhaseTrace tr;
   // src/join_base.cpp:196: check_equal(uids.size(), paths0.size) - before any work on the index
@@ -1428,11 +1551,12 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     sp.n_perm_blocks = ex->Iw / 32;
     size_t budget = (size_t)24 << 30;  // device bytes a table of per-permutation counts may take (GCRE_PRECOUNT_MAX_MB overrides)
     if (const char* mb = std::getenv("GCRE_PRECOUNT_MAX_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
-    // kept rows take their counts along (join_sparse.cuh) when the join writes all of them; GCRE_TEST_EMIT=0 (test hook) turns it off
+    // kept rows take their counts along (join_sparse.cuh) when the join writes ALL of them (every result row is written only
+    // when path_idx is the running sum of the counts: res_is_prefix); GCRE_TEST_EMIT=0 (test hook) turns it off
     const char* emit_env = std::getenv("GCRE_TEST_EMIT");
     // <= 512 permutations: the split-carrier kernel (join_sparse_sc.cuh) runs instead and neither writes nor reads count tables
     const bool few_perms = sparse_sc_enabled(ex->Ip, sp.n_perm_blocks);
-    const bool emit = !few_perms && keep && pair_lo == 0 && pair_hi == total && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
+    const bool emit = !few_perms && keep && pair_lo == 0 && pair_hi == total && us->res_is_prefix && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
                       (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
     int pc_mode = emit ? PRECOUNT_NO : precount_mode(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget);
     if (few_perms && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;  // the split-carrier kernel is the better form there

@@ -64,7 +64,8 @@ constexpr int min_blocks(int m) { return m == 1 ? GCRE_SPARSE_MB1 : GCRE_SPARSE_
 // patient index n, whose row of the patient-major mask matrix is all zero - so lists can be consumed eight carriers
 // at a time with one 16-byte load and no tail handling.
 struct SparseView {
-  uint32_t* off = nullptr;    // [size*M + 1]  padded prefix (entries), multiples of 8
+  unsigned long long* off = nullptr;  // [size*M + 1]  padded prefix (entries), multiples of 8; 64-bit: a kept level-3 set at 100,000
+                                      // patients holds ~1e9 carriers and larger cohorts pass 2^32
   uint32_t* len = nullptr;    // [size*M]      true carrier counts
   void* car = nullptr;        // [off[size*M]] patient indices: u16 when n <= 65,535, else u32
   uint32_t* ncase = nullptr;  // [size*M] carriers < n_cases (a prefix of the ascending list)
@@ -78,8 +79,8 @@ struct SparseView {
 };
 
 struct SparseParams {
-  const uint32_t* off0; const uint32_t* len0; const void* car0; const uint32_t* ncase0;   // car: CT[] (u16 or u32)
-  const uint32_t* off1; const uint32_t* len1; const void* car1; const uint32_t* ncase1;
+  const unsigned long long* off0; const uint32_t* len0; const void* car0; const uint32_t* ncase0;   // car: CT[] (u16 or u32)
+  const unsigned long long* off1; const uint32_t* len1; const void* car1; const uint32_t* ncase1;
   int n;                                  // patients; also the sentinel carrier index (zero row of pt)
   const unsigned long long* unit_prefix;  // [U+1] running sum of ceil(count/PB)
   const uint32_t* unit_idx;               // [n_units_total] upstream row of every unit (replaces a binary search per unit)
@@ -96,7 +97,7 @@ struct SparseParams {
 // ---- view construction ----------------------------------------------------------------------------------------------
 // per (row, half): true carrier count and the padded count (multiple of 8) that is prefix-summed into offsets
 __global__ void half_popcount_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, uint32_t* __restrict__ len,
-                                     uint32_t* __restrict__ padded) {
+                                     unsigned long long* __restrict__ padded) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= n_items) return;
@@ -112,12 +113,12 @@ __global__ void half_popcount_kernel(const uint64_t* __restrict__ rows, long lon
 
 template <typename CT>
 __global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long n_items, int Wp, int n_cases, int sentinel,
-                                   const uint32_t* __restrict__ off, CT* __restrict__ car, uint32_t* __restrict__ ncase) {
+                                   const unsigned long long* __restrict__ off, CT* __restrict__ car, uint32_t* __restrict__ ncase) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= n_items) return;
   const uint64_t* p = rows + (size_t)warp * Wp;
-  uint32_t pos = off[warp];
+  unsigned long long pos = off[warp];
   unsigned nc = 0;
   for (int k0 = 0; k0 < Wp; k0 += 32) {
     const int k = k0 + lane;
@@ -130,7 +131,7 @@ __global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long 
       const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
-    uint32_t o = pos + incl - c;
+    unsigned long long o = pos + incl - c;
     while (w) {
       const int b = __ffsll((long long)w) - 1;
       w &= w - 1;
@@ -141,8 +142,8 @@ __global__ void build_lists_kernel(const uint64_t* __restrict__ rows, long long 
     pos += __shfl_sync(0xffffffffu, incl, 31);
   }
   // pad with the sentinel up to the next list start
-  const uint32_t end = off[warp + 1];
-  for (uint32_t o = pos + lane; o < end; o += 32) car[o] = (CT)sentinel;
+  const unsigned long long end = off[warp + 1];
+  for (unsigned long long o = pos + lane; o < end; o += 32) car[o] = (CT)sentinel;
   nc = __reduce_add_sync(0xffffffffu, nc);
   if (lane == 0) ncase[warp] = nc;
 }
@@ -217,7 +218,7 @@ __device__ __forceinline__ void load8(const uint32_t* p, uint32_t (&c)[8]) {
 
 // Pre-count table of a path set (see the header): one warp per (item, permutation block).
 template <typename CT>
-__global__ void __launch_bounds__(128) build_precount_kernel(const uint32_t* __restrict__ off, const CT* __restrict__ car, long long n_items, int n_perm_blocks,
+__global__ void __launch_bounds__(128) build_precount_kernel(const unsigned long long* __restrict__ off, const CT* __restrict__ car, long long n_items, int n_perm_blocks,
                                                              const uint32_t* __restrict__ pt, int Iw, uint32_t* __restrict__ pcnt) {
   const int lane = threadIdx.x & 31;
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(128) build_precount_kernel(const uint32_t* __r
   const long long item = w / n_perm_blocks;
   const int pb = (int)(w % n_perm_blocks);
   const uint32_t* pt_lane = pt + pb * 32 + lane;
-  const uint32_t o = off[item], plen = off[item + 1] - o;
+  const unsigned long long o = off[item];
+  const uint32_t plen = (uint32_t)(off[item + 1] - o);
   uint32_t pl[8], c16[16];
 #pragma unroll
   for (int j = 0; j < 8; j++) pl[j] = 0;
@@ -387,9 +389,10 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
         uint32_t acc[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) acc[i] = 0;
-        const uint32_t o = s.off0[item], plen = s.off0[item + 1] - o;
+        const CT* lst = car0 + s.off0[item];
+        const uint32_t plen = (uint32_t)(s.off0[item + 1] - s.off0[item]);
 #pragma unroll 1
-        for (uint32_t i = 0; i < plen; i += 8) add8(acc, car0 + o + i, i + 8 >= plen);
+        for (uint32_t i = 0; i < plen; i += 8) add8(acc, lst + i, i + 8 >= plen);
 #pragma unroll
         for (int i = 0; i < 16; i++) s_base[h][i][tid] = acc[i];
       }
@@ -415,7 +418,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
         // joined half h = upstream half h | partner half hh   (src/methods.h:137-145)
         const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
         const size_t item = (size_t)loc * M + hh;
-        const uint32_t o = s.off1[item], len = s.len1[item];
+        const CT* lst1 = car1 + s.off1[item];
+        const uint32_t len = s.len1[item];
         const uint64_t* p0h = p0row + h * Wp;
         uint32_t ndh = 0, ncnh = 0;
         uint32_t qn = 0;  // carriers waiting in the queue (warp-uniform)
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
         for (uint32_t i0 = 0; i0 < len; i0 += 32) {
           const uint32_t i = i0 + lane;
           const bool valid = i < len;
-          const uint32_t c = valid ? (uint32_t)car1[o + i] : 0u;
+          const uint32_t c = valid ? (uint32_t)lst1[i] : 0u;
           const uint32_t w0 = valid ? __ldg(reinterpret_cast<const uint32_t*>(p0h) + (c >> 5)) : 0u;
           // delta: carriers not yet in the upstream row are added to the base; PC: carriers already in it are subtracted
           const bool keep = valid && (((w0 >> (c & 31)) & 1u) != 0u) == PC;

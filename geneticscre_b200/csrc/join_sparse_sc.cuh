@@ -137,14 +137,15 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
 #pragma unroll
       for (int i = 0; i < 16; i++) acc[i] = 0;
       const size_t item = (size_t)idx * M + h;
-      const uint32_t o = s.off0[item], plen = s.off0[item + 1] - o;
+      const CT* lst0 = car0 + s.off0[item];
+      const uint32_t plen = (uint32_t)(s.off0[item + 1] - s.off0[item]);
       const uint32_t t0h = s.len0[item], nc0h = s.ncase0[item];
 #pragma unroll 1
       for (uint32_t i = 0; i < plen; i += B) {
         uint32_t x[8];
         if (i + sub * 8 < plen) {
           uint32_t c[8];
-          load8(car0 + o + i + sub * 8, c);
+          load8(lst0 + i + sub * 8, c);
 #pragma unroll
           for (int q = 0; q < 8; q++) x[q] = __ldg(pt_lane + c[q] * (uint32_t)Iw);
         } else {
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
         for (int i = 0; i < 16; i++) c16[i] = 0;
         const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
         const size_t item = (size_t)loc * M + hh;
-        const uint32_t o = s.off1[item], len = s.len1[item];
+        const CT* lst1 = car1 + s.off1[item];
+        const uint32_t len = s.len1[item];
         const uint64_t* p0h = p0row + h * Wp;
         uint32_t ndh = 0, ncnh = 0;
         uint32_t qn = 0;
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
         for (uint32_t i0 = 0; i0 < len; i0 += 32) {
           const uint32_t i = i0 + lane;
           const bool valid = i < len;
-          const uint32_t c = valid ? (uint32_t)car1[o + i] : 0u;
+          const uint32_t c = valid ? (uint32_t)lst1[i] : 0u;
           const uint32_t w0 = valid ? __ldg(reinterpret_cast<const uint32_t*>(p0h) + (c >> 5)) : 0u;
           const bool keep = valid && !((w0 >> (c & 31)) & 1u);
           const unsigned km = __ballot_sync(0xffffffffu, keep);

@@ -32,6 +32,18 @@ __global__ void place_rows_kernel(const uint64_t* __restrict__ src, uint32_t row
   out[(size_t)r * row_words + k] = src[(size_t)r * wsrc + k];
 }
 
+// Bits at patient indices >= n cannot mean anything (there are n = num_cases + num_ctrls patients); packed inputs and raw
+// row writes may carry them.  Cleared on entry: the sparse kernels index the patient-major masks by patient, and the padding
+// word of a half-row (Wp is W64 rounded up to 2) must stay zero.
+__global__ void mask_tail_kernel(uint64_t* __restrict__ rows_io, long long n_halves, int Wp, int W64, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_halves) return;
+  uint64_t* p = rows_io + (size_t)i * Wp;
+  const int rem = n & 63;
+  if (rem && W64 > 0) p[W64 - 1] &= (1ull << rem) - 1ull;
+  for (int k = W64; k < Wp; k++) p[k] = 0ull;
+}
+
 // device rows -> unpadded host layout uint64[rows][W64*M]
 template <int M>
 __global__ void unpad_rows_kernel(const uint64_t* __restrict__ rows_in, uint32_t rows, int Wp, int W64, uint64_t* __restrict__ out) {

@@ -17,6 +17,12 @@
 namespace gcre {
 
 constexpr int VT_THREADS = 256;
+// "probabilities <= own" is decided with this tolerance on the log-probabilities (= 1e-7 relative on the probabilities, the
+// relErr of R's own fisher.test).  Exact ties between different outcomes are common (P(x+1)/P(x) = 1 has integer solutions,
+// and every symmetric table has them); evaluated exactly, the reference's `prob_dist <= x` includes them, while its float
+// comparison keeps or drops them by dhyper's last-bit rounding.  With the tolerance the table equals the exact-arithmetic
+// evaluation of getValuesTable (tests/test_value_table.py checks it against big-integer combinatorics).
+constexpr double VT_TIE_TOL = 1e-7;
 
 __device__ __forceinline__ double vt_logp(const double* __restrict__ lf, int nc, int nt, int i, int x) {
   // (lchoose(nc, x) + lchoose(nt, i - x)) - lchoose(nc + nt, i), each lchoose(a, b) = (lf[a] - lf[b]) - lf[a - b]
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(VT_THREADS) value_table_kernel(const double* _
 
     // 3. two-sided sums by binary search, -log, store on the anti-diagonal of the R layout
     for (int k = threadIdx.x; k < m; k += VT_THREADS) {
-      const double v = logp[k];
+      const double v = logp[k] + VT_TIE_TOL;
       // left part ascending: number of entries <= v
       int a = 0, bnd = kmax + 1;
       while (a < bnd) {

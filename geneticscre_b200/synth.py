@@ -93,20 +93,15 @@ def make_perm_masks(n_cases: int, n_ctrls: int, n_perms: int, seed: int) -> np.n
 
 
 def log_factorials(n: int) -> np.ndarray:
-    """log(k!) for k = 0..n.  Taken from the engine library's host routine when it is built (so the device generator and
-    this restatement decide exact probability ties identically), else from math.lgamma."""
-    try:
-        import ctypes
+    """log(k!) for k = 0..n from libm's lgamma (math.lgamma) - the same routine the engine's host code calls
+    (gcre_log_factorial_table: std::lgamma), so the device generator and this restatement start from identical doubles.
+    Pure Python on purpose: input preparation must not need the CUDA library (the CPU reference arm of bench.py uses it)."""
+    import math
 
-        from . import _lib
+    return np.array([math.lgamma(k + 1.0) for k in range(n + 1)], dtype=np.float64)
 
-        out = np.zeros(n + 1, dtype=np.float64)
-        _lib.check(_lib.load().gcre_log_factorial_table(int(n), out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
-        return out
-    except (RuntimeError, OSError):
-        import math
 
-        return np.array([math.lgamma(k + 1.0) for k in range(n + 1)], dtype=np.float64)
+VT_TIE_TOL = 1e-7  # as csrc/value_table.cuh: outcomes whose probabilities agree to 1e-7 relative are ties (R's fisher.test relErr)
 
 
 def make_value_table(n_cases: int, n_ctrls: int) -> np.ndarray:
@@ -114,10 +109,10 @@ def make_value_table(n_cases: int, n_ctrls: int) -> np.ndarray:
 
     For every total i the number of cases among i carriers is hypergeometric; the two-sided p of an outcome is the sum of
     all probabilities <= its own; infinities are replaced by (max finite + 1).  Log-probabilities come from a
-    log-factorial table (math.lgamma) and the "<= own" selection is made on the log-probabilities, in the same
-    association order as the device generator (csrc/value_table.cuh), so both select identical sets; they differ only in
-    exp() rounding and summation order (~1e-15).  The table need not match R's dhyper to the last ulp: oracle and GPU
-    consume the same table.
+    log-factorial table (math.lgamma) and the "<= own" selection is made on the log-probabilities with the tie tolerance
+    VT_TIE_TOL: exact ties between outcomes are common and belong to the sum when the reference's expression is evaluated
+    exactly (its own float comparison keeps or drops them by dhyper's last-bit rounding).  tests/test_value_table.py pins this
+    function and the device generator (csrc/value_table.cuh) to an exact big-integer evaluation and to scipy.stats.hypergeom.
     """
     n = n_cases + n_ctrls
     lf = log_factorials(n)
@@ -132,7 +127,7 @@ def make_value_table(n_cases: int, n_ctrls: int) -> np.ndarray:
         order = np.argsort(logp, kind="stable")
         ls = logp[order]
         csum = np.cumsum(np.exp(ls))
-        last = np.searchsorted(ls, ls, side="right") - 1  # last sorted position with a log-probability <= own
+        last = np.searchsorted(ls, ls + VT_TIE_TOL, side="right") - 1  # last sorted position with a probability <= own (ties included)
         two = np.empty_like(logp)
         two[order] = csum[last]
         with np.errstate(divide="ignore"):

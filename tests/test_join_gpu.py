@@ -342,27 +342,6 @@ def test_topk_launch_plan_paths(engine, oracles, method, kernel, top_k, monkeypa
     assert got["4"].info["launches"] >= 3
 
 
-@pytest.mark.parametrize("nc,nt", [(2, 2), (100, 100), (57, 131), (700, 300), (5000, 5000)])
-def test_device_value_table_matches_host_restatement(engine, nc, nt):
-    """getValuesTable (R/Utils.R:137-159) generated on the device vs the numpy restatement.
-
-    Floating point: the stated tolerance is 1e-10 relative (plus 1e-9 absolute for entries that are -log(1 +- rounding)):
-    both sides select the same probability sets (comparison on bit-identical log-probabilities) and differ only in exp()
-    rounding and summation order."""
-    ex = engine.JoinExec("method1", nc, nt, 1)
-    ex.generateValueTable()
-    got = ex.getValueTable()
-    want = synth.make_value_table(nc, nt)
-    assert got.shape == want.shape
-    assert np.isfinite(got).all()
-    # entries above ~700 are -log of sums in the denormal range (p < 1e-304), where exp() has no relative accuracy on
-    # either side (and R's dhyper neither); they only have to be "astronomically significant" on both sides
-    normal = want <= 700.0
-    np.testing.assert_allclose(got[normal], want[normal], rtol=1e-10, atol=1e-9)
-    assert (got[~normal] > 700.0).all()
-    assert abs(got.max() - want.max()) <= 1.0 + 1e-9
-
-
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("method", ["method1", "method2"])
 def test_many_permutations_span_several_blocks(engine, oracles, method, kernel):
@@ -487,3 +466,47 @@ def test_sparse_queue_drain_corner_cases(engine, oracles, method, pc, perms):
     for got, rows in out[1:]:
         helpers.assert_same_results(got, out[0][0])
         assert np.array_equal(rows, out[0][1])
+
+
+def test_exec_destroyed_before_its_children(engine):
+    """gcre_exec_destroy orphans the exec's path sets and join indices: destroying them later is legal, using them is an error."""
+    ex = engine.JoinExec("method1", 40, 41, 8)
+    ps = ex.createPathSet(5)
+    uid = engine.UidRelSet(1, [0], [0], [1], [0], [1]).make_resident(ex)
+    ex.close()  # the wrapper's exec handle is gone; the C path set and join index are still alive
+    out = np.zeros((5, 2), dtype=np.uint64)
+    import ctypes as C
+
+    assert _lib.load().gcre_pathset_download(ps._h, out.ctypes.data_as(C.POINTER(C.c_uint64))) == _lib.GCRE_ERR_ARG
+    uid.release()
+    del ps  # gcre_pathset_destroy on an orphan: must not touch the dead exec
+
+
+def test_load_rejects_columns_beyond_n(engine):
+    ex = engine.JoinExec("method1", 30, 31, 4)
+    ps = ex.createPathSet(2)
+    ps.load(np.ones((2, 61), dtype=np.int32))
+    with pytest.raises(_lib.GcreOutOfRange):
+        ps.load(np.ones((2, 62), dtype=np.int32))
+
+
+@pytest.mark.parametrize("kernel", [pytest.param(_lib.KERNEL_DENSE, id="dense"), pytest.param(_lib.KERNEL_SPARSE, id="sparse")])
+def test_packed_bits_beyond_n_are_dropped(engine, oracles, kernel):
+    """load_bits / set with bits at patient indices >= n: cleared on entry, so both kernel families score the n real patients."""
+    w = synth.make_workload(35, 35, 40, 120, 64, seed=31, max_path_length=3, real_table=True, max_freq=0.2, zero_frac=0.2)
+    n = w.n_patients  # 70: the last word holds 6 patients
+    dirty = w.gene_bits.copy()
+    dirty[:, -1] |= np.uint64(0xFFFFFFFFFFFFFFFF) << np.uint64(n % 64)
+    ex = engine.JoinExec("method2", w.n_cases, w.n_ctrls, w.n_perms)
+    ex.kernel = kernel
+    ps = ex.createPathSet(dirty.shape[0])
+    ps.load_bits(dirty)
+    got = ps.to_numpy()
+    assert np.array_equal(got[:, : w.gene_bits.shape[1]], w.gene_bits) and not got[:, w.gene_bits.shape[1]:].any()
+    ps.set(3, np.concatenate([dirty[5], dirty[6]]))
+    assert np.array_equal(ps[3], np.concatenate([w.gene_bits[5], w.gene_bits[6]]))
+    wd = synth.Workload(w.n_cases, w.n_ctrls, w.n_perms, dirty, np.ascontiguousarray(dirty[w.net.ents2]), w.perm_masks, w.value_table, w.net)
+    want, _, _ = helpers.run_schedule(oracles.OracleExec, oracles.UidRelSet, w, "method2", 3, 5)
+    got_r, _, _ = run_engine(engine, wd, "method2", 3, 5, kernel)
+    for lvl in want:
+        helpers.assert_same_results(got_r[lvl], want[lvl], what=f"dirty tail bits L{lvl}")
