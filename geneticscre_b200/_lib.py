@@ -26,10 +26,15 @@ class ExecInfoC(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("method", "num_cases", "num_ctrls", "width_ul", "iterations", "iters_requested", "device", "sm_count")]
 
 
+class DecoratedC(C.Structure):
+    _fields_ = [("pvalue", C.c_double), ("score", C.c_double), ("cases1", C.c_int32), ("ctrls1", C.c_int32), ("cases2", C.c_int32), ("ctrls2", C.c_int32)]
+
+
 class JoinOptsC(C.Structure):
     _fields_ = [("uid_begin", C.c_uint32), ("uid_end", C.c_uint32), ("kernel", C.c_int32), ("skip_host_perm", C.c_int32),
                 ("pairs_scored", C.c_uint64), ("kernel_ms", C.c_double), ("kernel_used", C.c_int32), ("launches", C.c_int32),
-                ("precounted", C.c_int32), ("split_carrier", C.c_int32)]
+                ("precounted", C.c_int32), ("split_carrier", C.c_int32), ("screened", C.c_int32), ("reserved", C.c_int32),
+                ("exact_units", C.c_uint64), ("total_units", C.c_uint64)]
 
 
 # every symbol include/gcre_b200.h declares: name -> (restype, argtypes)
@@ -43,6 +48,7 @@ SYMBOLS = {
     "gcre_exec_create": (_I, [_I, _I, _I, _I, _I, C.POINTER(_VP)]),
     "gcre_exec_destroy": (_I, [_VP]),
     "gcre_exec_get_info": (_I, [_VP, C.POINTER(ExecInfoC)]),
+    "gcre_exec_decorated_exact": (_I, [_VP, C.POINTER(C.c_uint64), _U32, C.POINTER(DecoratedC)]),
     "gcre_exec_set_stream": (_I, [_VP, _VP]),
     "gcre_exec_set_value_table": (_I, [_VP, C.POINTER(C.c_double), _I, _I]),
     "gcre_exec_generate_value_table": (_I, [_VP]),

@@ -25,7 +25,9 @@
 #include "join_dense.cuh"
 #include "join_sparse.cuh"
 #include "join_sparse_sc.cuh"
+#include "join_screen.cuh"
 #include "value_table.cuh"
+#include "decorated.cuh"
 
 using namespace gcre;
 
@@ -336,11 +338,15 @@ struct gcre_exec {
   float* d_diagF = nullptr;
   double* d_diagDM = nullptr;
   long long diag_cap = -1;
+  float2* d_env = nullptr;       // envelopes of the permutation look-up table rows (join_screen.cuh), built on first use
+  long long env_cap = -1;
+  float* d_thr = nullptr;        // per-lane screening thresholds [Iw]
   // outputs / scratch
   int* d_perm_max = nullptr;
   unsigned long long* d_topk = nullptr;  // [0] self-tightening candidate threshold, [1..64] its hash-bucket maxima (JoinParams::slots)
-  unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total, [2..3] 64-bit work counter of the sparse kernel
-  DevBuf cand, scratch, scan_tmp;
+  unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total, [2..3] 64-bit work counter of the sparse kernel,
+                                  // [4] seed entries, [5] retry entries of a screened join, [6..7] work counter of its exact passes
+  DevBuf cand, scratch, scan_tmp, retry, seed;
   unsigned* h_scalars = nullptr;  // pinned
   // path sets and join indices created from this exec: gcre_exec_destroy frees their device memory and orphans them (ex =
   // nullptr), so destroying the exec first is legal and a later gcre_pathset_destroy only deletes the host object
@@ -383,6 +389,7 @@ static void drop_view(gcre_pathset* ps) {
   dev_free(ps->ex, ps->view.ncase);
   dev_free(ps->ex, ps->view.car);
   dev_free(ps->ex, ps->view.pcnt);
+  dev_free(ps->ex, ps->view.prange);
   ps->view = SparseView();
 }
 
@@ -492,7 +499,7 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
     CK(pool_stream(device, &ex->copy_stream));
     CK(pool_event(device, false, &ex->ev_copy));
     CK(pool_event(device, false, &ex->ev_order));
-    for (DevBuf* b : {&ex->cand, &ex->scratch, &ex->scan_tmp}) b->owner = ex;
+    for (DevBuf* b : {&ex->cand, &ex->scratch, &ex->scan_tmp, &ex->retry, &ex->seed}) b->owner = ex;
     CK(dev_alloc(ex, (void**)&ex->d_masks, std::max<size_t>((size_t)iters * ex->W64, 1) * 8));
     CK(dev_alloc(ex, (void**)&ex->d_pm, (size_t)ex->Wp * ex->Ip * 8));
     CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)iters * ex->W64, 1) * 8, ex->stream));
@@ -536,8 +543,10 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
     ex->uidsets.clear();
   }
   for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
-                  (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk})
+                  (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk, (void*)ex->d_env, (void*)ex->d_thr})
     dev_free(ex, p);
+  ex->retry.release();
+  ex->seed.release();
   ex->cand.release();
   ex->scan_tmp.release();
   ex->scratch.release();
@@ -738,6 +747,42 @@ extern "C" int gcre_exec_get_value_table(const gcre_exec* ex, double* out, int r
   CK(cudaMemcpyAsync(out, ex->d_vt, (size_t)rows * cols * 8, cudaMemcpyDeviceToHost, ex->stream));
   CK(cudaStreamSynchronize(ex->stream));
   return GCRE_OK;
+}
+
+// computeDecoratedPvalue (R/DecoratedPvalue.R:198-304) in its exact limit for n_items splits; see decorated.cuh.
+extern "C" int gcre_exec_decorated_exact(gcre_exec* ex, const uint64_t* rows, uint32_t n_items, gcre_decorated* out) {
+  static_assert(sizeof(gcre_decorated) == sizeof(DecoratedOut), "gcre_decorated layout");
+  if (!ex || ((!rows || !out) && n_items)) return fail(GCRE_ERR_ARG, "null argument");
+  CKS(use_device(ex));
+  if (!ex->d_vt) return fail(GCRE_ERR_ASSERT, "assertion");  // no value table set
+  if (!n_items) return GCRE_OK;
+  const size_t per_item = 2 * ((size_t)ex->n + 1) * 8;                                  // scratch: two probability vectors
+  const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_items, ((size_t)256 << 20) / per_item));
+  void *d_rows = nullptr, *d_scr = nullptr, *d_out = nullptr;
+  int rc = [&]() -> int {
+    CK(dev_alloc(ex, &d_rows, (size_t)chunk * 4 * ex->W64 * 8));
+    CK(dev_alloc(ex, &d_scr, (size_t)chunk * per_item));
+    CK(dev_alloc(ex, &d_out, (size_t)chunk * sizeof(DecoratedOut)));
+    for (uint32_t i0 = 0; i0 < n_items; i0 += chunk) {
+      const uint32_t ni = std::min(chunk, n_items - i0);
+      CK(cudaMemcpyAsync(d_rows, rows + (size_t)i0 * 4 * ex->W64, (size_t)ni * 4 * ex->W64 * 8, cudaMemcpyHostToDevice, ex->stream));
+      if (ex->M == 1)
+        decorated_exact_kernel<1><<<ni, DEC_THREADS, 0, ex->stream>>>((const uint64_t*)d_rows, ni, ex->W64, ex->n_cases, ex->n_ctrls, ex->d_vt, ex->vt_rows,
+                                                                      ex->vt_cols, (double*)d_scr, (DecoratedOut*)d_out);
+      else
+        decorated_exact_kernel<2><<<ni, DEC_THREADS, 0, ex->stream>>>((const uint64_t*)d_rows, ni, ex->W64, ex->n_cases, ex->n_ctrls, ex->d_vt, ex->vt_rows,
+                                                                      ex->vt_cols, (double*)d_scr, (DecoratedOut*)d_out);
+      CK(cudaGetLastError());
+      LAUNCHED();
+      CK(cudaMemcpyAsync(out + i0, d_out, (size_t)ni * sizeof(DecoratedOut), cudaMemcpyDeviceToHost, ex->stream));
+      CK(cudaStreamSynchronize(ex->stream));
+    }
+    return GCRE_OK;
+  }();
+  dev_free(ex, d_rows);
+  dev_free(ex, d_scr);
+  dev_free(ex, d_out);
+  return rc;
 }
 
 static int rebuild_mask_layouts(gcre_exec* ex) {
@@ -1146,6 +1191,9 @@ static int ensure_diag(gcre_exec* ex, long long t_needed) {
   ex->d_diagF = nullptr;
   ex->d_diagDM = nullptr;
   ex->diag_cap = -1;
+  dev_free(ex, ex->d_env);
+  ex->d_env = nullptr;
+  ex->env_cap = -1;
   const size_t entries = (size_t)(cap + 1) * (size_t)(cap + 2) / 2;
   {
     // (cap+1)(cap+2)/2 entries of 12 (method 1) or 16 (method 2) bytes: 26-34 GB at 65,535 carriers per half-row
@@ -1163,6 +1211,24 @@ static int ensure_diag(gcre_exec* ex, long long t_needed) {
   CK(cudaGetLastError());
       LAUNCHED();
   ex->diag_cap = cap;
+  return GCRE_OK;
+}
+
+// envelopes of the permutation look-up rows for the screening kernel (join_screen.cuh); follows ensure_diag
+static int ensure_env(gcre_exec* ex) {
+  if (ex->d_env && ex->env_cap == ex->diag_cap) return GCRE_OK;
+  dev_free(ex, ex->d_env);
+  ex->d_env = nullptr;
+  ex->env_cap = -1;
+  const long long cap = ex->diag_cap;
+  if (cap < 0) return fail(GCRE_ERR_ARG, "no value table layout to build envelopes from");
+  const size_t entries = (size_t)(cap + 1) * (size_t)(cap + 2) / 2;
+  CK(dev_alloc(ex, (void**)&ex->d_env, entries * sizeof(float2)));
+  if (ex->M == 1) build_env_kernel<float><<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_diagF, (unsigned)cap, ex->n_cases, ex->n, ex->d_env);
+  else build_env_kernel<double><<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_diagDM, (unsigned)cap, ex->n_cases, ex->n, ex->d_env);
+  CK(cudaGetLastError());
+  LAUNCHED();
+  ex->env_cap = cap;
   return GCRE_OK;
 }
 
@@ -1222,10 +1288,13 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
   CKS(materialize_zero(ps));
   {  // (re)build lists and stats; counts emitted with the rows stay - the rows have not changed
     uint32_t* pcnt = ps->view.pcnt;
+    uint32_t* prange = ps->view.prange;
     const unsigned long long gen = ps->view.pcnt_gen;
     ps->view.pcnt = nullptr;
+    ps->view.prange = nullptr;
     drop_view(ps);
     ps->view.pcnt = pcnt;
+    ps->view.prange = prange;
     ps->view.pcnt_gen = gen;
   }
   const long long items = (long long)ps->size * ex->M;
@@ -1280,7 +1349,9 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
 static int ensure_precount(gcre_exec* ex, gcre_pathset* ps) {
   if (ps->view.pcnt && ps->view.pcnt_gen == ex->mask_gen) return GCRE_OK;
   dev_free(ex, ps->view.pcnt);
+  dev_free(ex, ps->view.prange);  // (ranges of emitted counts belong to the table they were emitted with)
   ps->view.pcnt = nullptr;
+  ps->view.prange = nullptr;
   const long long items = (long long)ps->size * ex->M;
   const int nb = ex->Iw / 32;
   CK(dev_alloc(ex, (void**)&ps->view.pcnt, std::max<size_t>((size_t)items * nb, 1) * 2048));
@@ -1535,6 +1606,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, ex->Iw)) kernel = GCRE_KERNEL_DENSE;
   SparseParams sp;
   memset(&sp, 0, sizeof sp);
+  bool screen_on = false;
   if (kernel == GCRE_KERNEL_SPARSE) {
     CKS(ensure_patient_major(ex));
     // upstream operand: rows that came out of a KEEP join carry their counts and totals - no carrier lists needed
@@ -1560,6 +1632,13 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
                       (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
     int pc_mode = emit ? PRECOUNT_NO : precount_mode(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget);
     if (few_perms && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;  // the split-carrier kernel is the better form there
+    // Range-bound screening (join_screen.cuh): score-only joins whose upstream rows carry their counts AND count ranges.
+    // GCRE_SCREEN=0 turns it off; GCRE_TEST_SCREEN=1 (test hook) runs it on joins of any size.
+    {
+      const char* scr = std::getenv("GCRE_SCREEN");
+      screen_on = !keep && base_emitted && paths0->view.prange && !few_perms && pc_mode != PRECOUNT_YES && !(scr && *scr == '0');
+      if (screen_on && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;
+    }
     if (pc_mode == PRECOUNT_SAMPLE) {
       // how much of a partner row is already in its upstream row: 2,048 pairs spread over the join (~40 us incl. the read-back)
       JoinParams q;
@@ -1595,9 +1674,11 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
       CK(dev_alloc(ex, (void**)&paths_res->view.pcnt, items * sp.n_perm_blocks * 2048));
       CK(dev_alloc(ex, (void**)&paths_res->view.len, items * 4));
       CK(dev_alloc(ex, (void**)&paths_res->view.ncase, items * 4));
+      CK(dev_alloc(ex, (void**)&paths_res->view.prange, items * sp.n_perm_blocks * 128));
       sp.pcnt_res = paths_res->view.pcnt;
       sp.len_res = paths_res->view.len;
       sp.ncase_res = paths_res->view.ncase;
+      sp.prange_res = paths_res->view.prange;
     }
   }
 
@@ -1675,6 +1756,8 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   unsigned long long thr_key = score_key(-std::numeric_limits<double>::infinity());
   double kernel_ms = 0.0;
   int launches = 0;
+  bool screened = false;
+  unsigned long long screened_units = 0, exact_units = 0;
   for (size_t si = 0; si < plan.size(); si++) {
     const Seg seg = plan[si];
     const unsigned long long p = seg.b, pe = seg.e;
@@ -1688,22 +1771,67 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     if (sparse_k) {
       sp.unit_begin = p;
       sp.n_units = pe - p;
-      CK(cudaMemsetAsync(ex->d_scalars + 2, 0, 2 * sizeof(unsigned), ex->stream));
-      if (sparse_sc_applies(jp, sp)) CK(launch_join_sparse_sc(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
-      else CK(launch_join_sparse(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
-      LAUNCHED();
-      launches++;
+      CK(cudaMemsetAsync(ex->d_scalars + 2, 0, 6 * sizeof(unsigned), ex->stream));
+      const bool screen_seg = screen_on && (sp.n_units >= screen::MIN_UNITS || std::getenv("GCRE_TEST_SCREEN") != nullptr);
+      if (screen_seg) {
+        // seed (exact, every stride-th unit) -> thresholds -> screening pass over all units -> exact pass over what it flagged
+        int stride = screen::SEED_STRIDE;
+        if (const char* e = std::getenv("GCRE_TEST_SCREEN_STRIDE")) stride = std::max(1, std::atoi(e));
+        const unsigned long long n_seed = (sp.n_units + stride - 1) / stride * (unsigned long long)sp.n_perm_blocks;
+        const unsigned long long n_all = sp.n_units * (unsigned long long)sp.n_perm_blocks;
+        if (n_all > 0xfffffff0ull) return fail(GCRE_ERR_ARG, "join too large: more than 2^32 work items");
+        CKS(ensure_env(ex));
+        if (!ex->d_thr) CK(dev_alloc(ex, (void**)&ex->d_thr, (size_t)ex->Iw * 4));
+        CKS(ex->seed.ensure((size_t)n_seed * sizeof(RetryEntry)));
+        CKS(ex->retry.ensure((size_t)n_all * sizeof(RetryEntry)));
+        screen_seed_list_kernel<<<grid_for((long long)n_seed, 256), 256, 0, ex->stream>>>(sp.unit_begin, sp.n_units, stride, sp.n_perm_blocks,
+                                                                                          (RetryEntry*)ex->seed.p, ex->d_scalars + 4);
+        CK(cudaGetLastError());
+        LAUNCHED();
+        SparseParams sr = sp;
+        sr.retry = (const RetryEntry*)ex->seed.p;
+        sr.retry_count = ex->d_scalars + 4;
+        sr.work_counter = (unsigned long long*)(ex->d_scalars + 6);
+        CK(launch_join_sparse_retry(ex->stream, jp, sr, ex->M, ex->sm_count));
+        LAUNCHED();
+        screen_thresholds_kernel<<<grid_for(ex->Iw, 128), 128, 0, ex->stream>>>(ex->d_perm_max, ex->iters, ex->Iw, ex->d_thr);
+        CK(cudaGetLastError());
+        LAUNCHED();
+        ScreenParams zp;
+        zp.prange0 = paths0->view.prange;
+        zp.env = ex->d_env;
+        zp.thr = ex->d_thr;
+        zp.retry = (RetryEntry*)ex->retry.p;
+        zp.retry_count = ex->d_scalars + 5;
+        if (ex->M == 1) CK(launch_join_screen<1>(ex->stream, jp, sp, zp, ex->sm_count));
+        else CK(launch_join_screen<2>(ex->stream, jp, sp, zp, ex->sm_count));
+        LAUNCHED();
+        CK(cudaMemsetAsync(ex->d_scalars + 6, 0, 2 * sizeof(unsigned), ex->stream));
+        sr.retry = (const RetryEntry*)ex->retry.p;
+        sr.retry_count = ex->d_scalars + 5;
+        CK(launch_join_sparse_retry(ex->stream, jp, sr, ex->M, ex->sm_count));
+        LAUNCHED();
+        launches += 5;
+        screened_units += n_all;
+        screened = true;
+      } else {
+        if (sparse_sc_applies(jp, sp)) CK(launch_join_sparse_sc(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
+        else CK(launch_join_sparse(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
+        LAUNCHED();
+        launches++;
+      }
     } else {
       jp.pair_begin = p;
       jp.pair_end = pe;
       CKS(launch_join_dense(ex, jp, keep, &launches));
     }
     CK(cudaEventRecord(ex->ev1, ex->stream));
-    CK(cudaMemcpyAsync(ex->h_scalars, ex->d_scalars, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaMemcpyAsync(ex->h_scalars, ex->d_scalars, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, ex->stream));
     CK(cudaStreamSynchronize(ex->stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ex->ev0, ex->ev1));
     kernel_ms += ms;
+    exact_units += (unsigned long long)ex->h_scalars[4] + ex->h_scalars[5];
     if (ex->h_scalars[0] > cap) {
       // budget overflow: redo this range in safe chunks (growing x8 up to 4M pairs)
       unsigned long long chunk = redo_first;
@@ -1769,6 +1897,9 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     opts->launches = launches;
     opts->precounted = sp.pcnt1 != nullptr;
     opts->split_carrier = kernel == GCRE_KERNEL_SPARSE && sparse_sc_applies(jp, sp);
+    opts->screened = screened ? 1 : 0;
+    opts->exact_units = screened ? exact_units : 0;
+    opts->total_units = screened_units;
   }
   return GCRE_OK;
 }

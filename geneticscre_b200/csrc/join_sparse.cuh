@@ -76,6 +76,8 @@ struct SparseView {
   // [item][perm block][q = 0..3][lane][4] u32 = packed u16 pairs (registers 4q..4q+3 of GCRE_C16_REG) - 2 KB per block
   uint32_t* pcnt = nullptr;
   unsigned long long pcnt_gen = 0;  // exec->mask_gen the table was built for
+  // min | max << 16 over the 32 permutations of every lane of the emitted counts: [item][perm block][lane] (join_screen.cuh)
+  uint32_t* prange = nullptr;
 };
 
 struct SparseParams {
@@ -92,7 +94,30 @@ struct SparseParams {
   uint32_t* pcnt_res;                     // KEEP: where to emit the counts / carrier totals of the kept rows, else null
   uint32_t* len_res;
   uint32_t* ncase_res;
+  uint32_t* prange_res;                   // KEEP: per-lane min | max << 16 of the emitted counts (join_screen.cuh), else null
+  // RETRY kernels (join_screen.cuh): work items are the entries of this list (unit, permutation block, partner mask)
+  const struct RetryEntry* retry;
+  const unsigned* retry_count;
 };
+
+struct RetryEntry {
+  uint32_t unit;            // absolute unit index
+  uint32_t pb;              // permutation block
+  unsigned long long mask;  // partners of the unit (bit j - j0) that need exact scoring
+};
+
+// min / max over the 32 u16 counts a lane holds in 16 packed registers -> min | max << 16
+__device__ __forceinline__ uint32_t range16(const uint32_t (&v)[16]) {
+  uint32_t mn = __vimin3_u16x2(v[0], v[1], v[2]), mx = __vimax3_u16x2(v[0], v[1], v[2]);
+#pragma unroll
+  for (int i = 3; i < 15; i += 2) {
+    mn = __vimin3_u16x2(mn, v[i], v[i + 1]);
+    mx = __vimax3_u16x2(mx, v[i], v[i + 1]);
+  }
+  mn = __vminu2(mn, v[15]);
+  mx = __vmaxu2(mx, v[15]);
+  return min(mn & 0xffffu, mn >> 16) | (max(mx & 0xffffu, mx >> 16) << 16);
+}
 
 // ---- view construction ----------------------------------------------------------------------------------------------
 // per (row, half): true carrier count and the padded count (multiple of 8) that is prefix-summed into offsets
@@ -255,7 +280,9 @@ __global__ void __launch_bounds__(128) build_precount_kernel(const unsigned long
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // CT = carrier index type of the list views: uint16_t (n <= 65,535) or uint32_t
-template <int M, bool KEEP, typename CT, bool PC>
+// RETRY: the work items are the entries of s.retry - units with a mask of the partners to score, permutation maxima only
+// (true scores, candidates and kept rows were handled by the screening kernel, join_screen.cuh)
+template <int M, bool KEEP, typename CT, bool PC, bool RETRY = false>
 __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_sparse_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse;
   const CT* car0 = static_cast<const CT*>(s.car0);
@@ -272,7 +299,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
   const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Wp = a.Wp, Iw = a.Iw;  // Iw: words per patient row of pt (a multiple of 32: every lane owns a valid word)
   const int row_words = Wp * M;
-  const unsigned long long n_work = s.n_units * (unsigned long long)s.n_perm_blocks;
+  const unsigned long long n_work = RETRY ? (unsigned long long)__ldg(s.retry_count) : s.n_units * (unsigned long long)s.n_perm_blocks;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint32_t* queue = s_queue[warp];
 
@@ -295,15 +322,25 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     if (lane == 0) g = atomicAdd(s.work_counter, 1ull);
     g = __shfl_sync(0xffffffffu, g, 0);
     if (g >= n_work) break;
-    const int pb = (int)(g / s.n_units);
-    const unsigned long long unit = s.unit_begin + (g % s.n_units);
+    unsigned long long retry_mask = ~0ull;
+    int pb;
+    unsigned long long unit;
+    if (RETRY) {
+      const RetryEntry e = s.retry[g];
+      pb = (int)e.pb;
+      unit = e.unit;
+      retry_mask = e.mask;
+    } else {
+      pb = (int)(g / s.n_units);
+      unit = s.unit_begin + (g % s.n_units);
+    }
     if (pb != pb_cur) {
       if (pb_cur >= 0) flush_best(pb_cur);
 #pragma unroll
       for (int b = 0; b < 32; b++) best[b] = 0.0f;
       pb_cur = pb;
     }
-    const bool first_pb = (pb == 0);
+    const bool first_pb = !RETRY && (pb == 0);
     const uint32_t idx = s.unit_idx[unit];
     const uint32_t sub = (uint32_t)(unit - s.unit_prefix[idx]);
     const uint32_t cnt_idx = (uint32_t)a.count[idx];
@@ -402,6 +439,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     bool base_done = false;
     // ---- partners ----
     for (uint32_t j = j0; j < j1; j++) {
+      if (RETRY && !((retry_mask >> (j - j0)) & 1ull)) continue;
       const uint32_t loc = loc0 + j;
       if (PC && j + 1 < j1) prefetch_partner(loc + 1);
       bool flip = true;
@@ -555,6 +593,12 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
             else __stcs(out + q * 32, make_uint4(s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q : 0][tid], s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 1 : 0][tid],
                                           s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 2 : 0][tid], s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 3 : 0][tid]));
           }
+          {  // the range of the lane's 32 counts: all the screening kernel of the next level reads of them
+            uint32_t v16[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) v16[i] = (M == 1) ? c16[i] : s_cnt[M == 2 ? h : 0][M == 2 ? i : 0][tid];
+            s.prange_res[((r * M + h) * s.n_perm_blocks + pb) * 32 + lane] = range16(v16);
+          }
           if (first_pb && lane == 0) {
             s.len_res[r * M + h] = t0[h == 0 ? 0 : M - 1] + nd[h == 0 ? 0 : M - 1];
             s.ncase_res[r * M + h] = nc0[h == 0 ? 0 : M - 1] + ncn[h == 0 ? 0 : M - 1];
@@ -672,6 +716,20 @@ static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinPara
   } else {
     if (keep) launch_sparse_pc<2, true>(grid, stream, jp, sp, wide);
     else launch_sparse_pc<2, false>(grid, stream, jp, sp, wide);
+  }
+  return cudaGetLastError();
+}
+
+// exact scoring of the entries of sp.retry (permutation maxima only); the entry count is read on the device
+static inline cudaError_t launch_join_sparse_retry(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, int sm_count) {
+  const unsigned grid = (unsigned)sm_count * sparse::min_blocks(M);
+  const bool wide = sparse_wide(sp.n);
+  if (M == 1) {
+    if (wide) join_sparse_kernel<1, false, uint32_t, false, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+    else join_sparse_kernel<1, false, uint16_t, false, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+  } else {
+    if (wide) join_sparse_kernel<2, false, uint32_t, false, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+    else join_sparse_kernel<2, false, uint16_t, false, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
   }
   return cudaGetLastError();
 }

@@ -6,7 +6,9 @@ without replacement among the patients the sub-path does not cover, the path is 
 decorated p-value is the share of redraws scoring at least as high as the real path (computeDecoratedPvalue,
 R/DecoratedPvalue.R:198-304).
 
-This is host-side post-processing of <= K * L * 2(L-1) sub-paths - not part of the join loop and not worth a kernel.  Only
+The exact, non-stratified limit also runs on the GPU (`decorated_exact_device`, csrc/decorated.cuh: one CTA per split, AND +
+popcount for the eight counts, hypergeometric weights by the ratio recurrence, value-table look-ups over the support); the
+Monte-Carlo and stratified modes are host utilities.  Only
 the number of redrawn carriers that fall among the cases matters, and that number is hypergeometric, so besides the
 reference's Monte-Carlo estimate (`n_permutations` redraws; R's `sample()` stream cannot be reproduced, a seeded numpy
 generator is used) the exact limit of that estimate is available (`n_permutations=None`): the tail probability is summed
@@ -150,8 +152,31 @@ def compute_decorated_pvalue(pos1, neg1, pos2, neg2, n_cases: int, n_ctrls: int,
     return DecoratedResult(pvalue, case_pos1 + case_neg1, ctrl_pos1 + ctrl_neg1, case_pos2 + case_neg2, ctrl_pos2 + ctrl_neg2, score)
 
 
+def decorated_exact_device(ex, splits) -> list[DecoratedResult]:
+    """Exact-limit decorated p-values of many splits in one call on the GPU (gcre_exec_decorated_exact, csrc/decorated.cuh).
+
+    ex: a JoinExec holding the value table (its method and cohort sizes are used); splits: iterable of
+    (pos1, neg1, pos2, neg2) boolean patient vectors as for :func:`compute_decorated_pvalue`."""
+    import ctypes as C
+
+    from . import _lib, synth
+
+    splits = list(splits)
+    n = ex.num_cases + ex.num_ctrls
+    if not splits:
+        return []
+    flat = np.stack([np.asarray(v, dtype=bool) for sp in splits for v in sp])
+    if flat.shape[1] != n:
+        raise ValueError("carrier vectors must have one entry per patient")
+    bits = np.ascontiguousarray(synth.pack_bits(flat))  # [4 * items][W64]
+    out = (_lib.DecoratedC * len(splits))()
+    _lib.check(ex._lib.gcre_exec_decorated_exact(ex._h, bits.ctypes.data_as(C.POINTER(C.c_uint64)), len(splits), out))
+    return [DecoratedResult(o.pvalue, o.cases1, o.ctrls1, o.cases2, o.ctrls2, o.score) for o in out]
+
+
 def decorated_pvalues_for_path(gene_rows: np.ndarray, signs, n_cases: int, n_ctrls: int, method: int, value_table: np.ndarray,
-                               n_permutations: int | None = None, rng: np.random.Generator | None = None, strata=None) -> list[dict]:
+                               n_permutations: int | None = None, rng: np.random.Generator | None = None, strata=None,
+                               device_exec=None) -> list[dict]:
     """All forward and backward splits of one path (R/DecoratedPvalue.R:123-180).
 
     gene_rows: bool/0-1 array [L][n] of the path's genes in order; signs: +1/-1 per gene (method 2 moves the genes with a
@@ -165,11 +190,17 @@ def decorated_pvalues_for_path(gene_rows: np.ndarray, signs, n_cases: int, n_ctr
     if method == 2:
         neg[signs == -1] = rows[signs == -1]
         pos[signs == -1] = False
-    out = []
+    splits, labels = [], []
     for j in range(1, L):  # forward: genes 1..j, then gene j+1
-        r = compute_decorated_pvalue(pos[:j].any(0), neg[:j].any(0), pos[j], neg[j], n_cases, n_ctrls, method, value_table, n_permutations, rng, strata)
-        out.append({"direction": "Forward", "subpath1": list(range(j)), "subpath2": j, **r.__dict__})
+        splits.append((pos[:j].any(0), neg[:j].any(0), pos[j], neg[j]))
+        labels.append({"direction": "Forward", "subpath1": list(range(j)), "subpath2": j})
     for j in range(L - 1, 0, -1):  # backward: genes L..j+1, then gene j
-        r = compute_decorated_pvalue(pos[j:].any(0), neg[j:].any(0), pos[j - 1], neg[j - 1], n_cases, n_ctrls, method, value_table, n_permutations, rng, strata)
-        out.append({"direction": "Backward", "subpath1": list(range(L - 1, j - 1, -1)), "subpath2": j - 1, **r.__dict__})
-    return out
+        splits.append((pos[j:].any(0), neg[j:].any(0), pos[j - 1], neg[j - 1]))
+        labels.append({"direction": "Backward", "subpath1": list(range(L - 1, j - 1, -1)), "subpath2": j - 1})
+    if device_exec is not None:  # all splits of the path in one kernel launch (exact mode, no strata)
+        if n_permutations is not None or strata is not None:
+            raise ValueError("the device path computes the exact, non-stratified limit")
+        results = decorated_exact_device(device_exec, splits)
+    else:
+        results = [compute_decorated_pvalue(*sp, n_cases, n_ctrls, method, value_table, n_permutations, rng, strata) for sp in splits]
+    return [{**lab, **r.__dict__} for lab, r in zip(labels, results)]

@@ -84,7 +84,19 @@ typedef struct {
   int32_t launches;         /* out: kernel launches made by this call */
   int32_t precounted;       /* out: 1 when the sparse kernel ran in its pre-counted-partner form (join_sparse.cuh) */
   int32_t split_carrier;    /* out: 1 when the <= 512-permutation form of the sparse kernel ran (join_sparse_sc.cuh) */
+  int32_t screened;         /* out: 1 when the range-bound screening kernel ran ahead of the exact one (join_screen.cuh) */
+  int32_t reserved;
+  uint64_t exact_units;     /* out: (unit, permutation block) work items the exact kernel scored for a screened join: seed + retries */
+  uint64_t total_units;     /* out: (unit, permutation block) work items of the join */
 } gcre_join_opts;
+
+/* One split of a reported path for the decorated p-value (R/DecoratedPvalue.R:198-304). */
+typedef struct {
+  double pvalue;            /* exact limit of the reference's Monte-Carlo estimate: P(re-scored path >= score) */
+  double score;             /* score of the real path from the value table */
+  int32_t cases1, ctrls1;   /* lst$cases1 / lst$controls1: the sub-path */
+  int32_t cases2, ctrls2;   /* lst$cases2 / lst$controls2: what the added gene contributes */
+} gcre_decorated;
 
 const char* gcre_last_error(void);
 const char* gcre_version(void);
@@ -99,6 +111,10 @@ int gcre_release_cached_memory(void);
 int gcre_exec_create(int method, int num_cases, int num_ctrls, int iters, int device, gcre_exec** out);
 int gcre_exec_destroy(gcre_exec* ex);
 int gcre_exec_get_info(const gcre_exec* ex, gcre_exec_info* out);
+/* computeDecoratedPvalue (R/DecoratedPvalue.R:198-304), non-stratified, in the exact limit of its Monte-Carlo estimate, for
+ * n_items splits at once against this exec's value table and method.  rows: uint64[n_items][4][ceil(n/64)] packed carrier
+ * vectors pos1, neg1 (sub-path), pos2, neg2 (added gene), patient c -> word c/64 bit c%64, cases first. */
+int gcre_exec_decorated_exact(gcre_exec* ex, const uint64_t* rows, uint32_t n_items, gcre_decorated* out);
 /* Run this exec's work on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the internal one. */
 int gcre_exec_set_stream(gcre_exec* ex, void* cuda_stream);
 

@@ -25,10 +25,16 @@ class _NoSplit(int):
     one-word-per-lane kernel - delta form, counts handed from level to level - runs on the small shapes too."""
 
 
+class _Screen(_NoSplit):
+    """As _NoSplit, plus the range-bound screening kernel (join_screen.cuh) forced onto joins of any size
+    (GCRE_TEST_SCREEN=1; the seed pass takes every 3rd unit so that seed, screening and retry passes all see work)."""
+
+
 SPARSE_PC = _Precount(_lib.KERNEL_SPARSE)
 SPARSE_NOSPLIT = _NoSplit(_lib.KERNEL_SPARSE)
+SPARSE_SCREEN = _Screen(_lib.KERNEL_SPARSE)
 KERNELS = [pytest.param(_lib.KERNEL_DENSE, id="dense"), pytest.param(_lib.KERNEL_SPARSE, id="sparse"), pytest.param(SPARSE_PC, id="sparse_pc"),
-           pytest.param(SPARSE_NOSPLIT, id="sparse_nosplit")]
+           pytest.param(SPARSE_NOSPLIT, id="sparse_nosplit"), pytest.param(SPARSE_SCREEN, id="sparse_screen")]
 PC_MODES = [pytest.param("0", id="delta"), pytest.param("1", id="precount")]
 
 
@@ -42,6 +48,11 @@ def _precount_mode(request, monkeypatch):
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", "0")
     if isinstance(k, _NoSplit):
         monkeypatch.setenv("GCRE_TEST_NO_SPLIT", "1")
+    if isinstance(k, _Screen):
+        monkeypatch.setenv("GCRE_TEST_SCREEN", "1")
+        monkeypatch.setenv("GCRE_TEST_SCREEN_STRIDE", "3")
+    else:
+        monkeypatch.setenv("GCRE_SCREEN", "0")
     if "pc" in params:
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", params["pc"])
 
@@ -103,6 +114,8 @@ def test_schedule_matches_oracle(engine, oracles, method, shape, kernel):
             assert got[lvl].info["precounted"] == isinstance(kernel, _Precount), "GCRE_TEST_PRECOUNT must select the kernel form"
         if kernel == _lib.KERNEL_SPARSE and not isinstance(kernel, _Precount) and w.net.levels[lvl].n_pairs > 0:
             assert got[lvl].info["split_carrier"] == (perms <= 512 and not isinstance(kernel, _NoSplit)), "<= 512 permutations run the split-carrier form"
+        if w.net.levels[lvl].n_pairs > 0 and lvl in ("4", "5"):
+            assert got[lvl].info["screened"] == isinstance(kernel, _Screen), "levels 4 and 5 are the screened joins (upstream rows carry counts + ranges)"
 
 
 @pytest.mark.parametrize("pc", PC_MODES)
