@@ -60,6 +60,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=2, choices=[1, 2],
                     help="e2e leg: 2 = submit the two methods from two host threads (uploads of one overlap joins of the other); 1 = sequential")
+    ap.add_argument("--perm-batch", type=int, default=4096,
+                    help="permutations scored per pass over the level schedule; more are processed as sequential batches of this size with the "
+                         "masks resident on the device (permutations are independent: maxima concatenate, the top-K is the same in every batch). "
+                         "Keeps the per-row count tables the joins hand from level to level (2 KB per row, half and 1,024 permutations) inside HBM")
+    ap.add_argument("--cpu-perms", type=int, default=1000, help="permutations the CPU baseline / parity leg scores (the reference's cost per pair*perm does not depend on the count)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: max(10, --steps))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per method for the baseline sample")
     for k, v in WORKLOAD.items():
@@ -98,6 +103,8 @@ def full_config(a, w, world):
     last = ["1a", "1b", "2", "3", "4", "5"][a.path_length]
     cfg = workload_config(a, w)
     cfg["permutations_total"] = w.n_perms * (world if shard_perms else 1)
+    if w.n_perms > a.perm_batch:
+        cfg["permutation_batches"] = f"{(w.n_perms + a.perm_batch - 1) // a.perm_batch} sequential batches of <= {a.perm_batch} permutations per GPU (masks resident)"
     cfg["parallelism"] = ("1 GPU" if world == 1 else
                           f"{world} GPUs, one block of {w.n_perms} permutations per GPU over all pairs; maxima merged with one NCCL allreduce(max)" if shard_perms else
                           f"{world} GPUs, level-{last} upstream rows sharded by pair count; one NCCL allreduce(max) per join + top-K gather")
@@ -181,16 +188,23 @@ def mem_available_bytes():
 
 
 def workload_file(w, a):
-    """The workload as an uncompressed .npz in shared memory (workers map it instead of regenerating it)."""
+    """The workload as an uncompressed .npz in shared memory (workers map it instead of regenerating it).  The CPU leg scores
+    the first min(n_perms, --cpu-perms) permutations."""
     import tempfile
+
+    cpu_perms = cpu_perm_count(w, a)
 
     d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
     path = os.path.join(d, f"gcre_bench_workload_{os.getpid()}.npz")
     net = w.net
-    np.savez(path, n_cases=w.n_cases, n_ctrls=w.n_ctrls, n_perms=w.n_perms, gene_bits=w.gene_bits, gene_bits2=w.gene_bits2,
-             perm_masks=w.perm_masks, value_table=w.value_table, n_genes=net.n_genes, edges_src=net.edges_src, edges_trg=net.edges_trg,
+    np.savez(path, n_cases=w.n_cases, n_ctrls=w.n_ctrls, n_perms=cpu_perms, gene_bits=w.gene_bits, gene_bits2=w.gene_bits2,
+             perm_masks=w.perm_masks[:cpu_perms], value_table=w.value_table, n_genes=net.n_genes, edges_src=net.edges_src, edges_trg=net.edges_trg,
              edges_sign=net.edges_sign, ents2=net.ents2, path_length=a.path_length)
     return path
+
+
+def cpu_perm_count(w, a):
+    return int(max(1, min(w.n_perms, getattr(a, "cpu_perms", 1000), getattr(a, "perm_batch", 4096))))
 
 
 def load_workload_file(path):
@@ -295,6 +309,7 @@ class ReferenceArm:
         from oracle import pyoracle as po  # (availability / ISA level only; the joins run in the workers)
 
         self.w, self.a, self.methods = w, a, methods
+        self.n_perms = cpu_perm_count(w, a)
         self.kind = "reference" if po.ref_available() else "port"
         self.variant = po.ref_variant()
         self.cores = (os.cpu_count() or 1) if self.kind == "reference" else 1
@@ -358,10 +373,10 @@ class ReferenceArm:
             share = r["pairs"] / max(lv.n_pairs, 1)
             fixed = min(t_fixed, 0.9 * r["seconds"])
             t_eff = r["seconds"] - fixed * (1.0 - share)
-            total_pp += r["pairs"] * w.n_perms
+            total_pp += r["pairs"] * self.n_perms
             total_t += t_eff
             detail[method] = {"pairs": r["pairs"], "of_level4_pairs": lv.n_pairs, "upstream_rows": r["x"], "seconds_measured": round(r["seconds"], 3),
-                              "seconds_charged": round(t_eff, 3), "pair_perm_per_s": r["pairs"] * w.n_perms / t_eff,
+                              "seconds_charged": round(t_eff, 3), "pair_perm_per_s": r["pairs"] * self.n_perms / t_eff,
                               "fixed_s_per_join": round(t_fixed, 3), "threads": self.threads[method],
                               "setup_levels_1_3_s": round(self.setup_s[method], 2)}
             if results:
@@ -375,7 +390,7 @@ class ReferenceArm:
                else "scalar C restatement (oracle/gcre_oracle.c), the reference build is absent")
         out = {"value": total_pp / total_t, "unit": "pair*perm/s", "cores": self.cores, "kind": self.kind,
                "sample": f"level-4 join (paths3 x paths2) per method ({'+'.join(self.methods)}): the whole join when it fits ~{3 * target_s:.0f} s, "
-                         f"else the first upstream rows sized for ~{target_s:.0f} s; {w.n_perms} perms, W64={(w.n_patients + 63) // 64}; {how}; "
+                         f"else the first upstream rows sized for ~{target_s:.0f} s; {self.n_perms} perms, W64={(w.n_patients + 63) // 64}; {how}; "
                          f"nthreads={self.threads['method1']} (method 2: {self.threads['method2']}); a prefix sample is charged its pro-rata share of the "
                          f"join's fixed cost (method 2 copies the (n+1)^2 table once per thread and join); run in worker subprocesses replaced every "
                          f"{self.joins_per_worker['method2']} method-2 joins (the reference never frees those copies)",
@@ -442,22 +457,26 @@ def emit_line(line):
         os.write(_REAL_STDOUT, data)
 
 
-def check_parity(ref_out, last_out, state, lv4, w, api):
+def check_parity(ref_out, last_out, state, lv4, w, api, cpu_perms, reset_masks):
     """GPU level-4 results against the reference's on the same inputs -> the `parity` object of the line (raises on mismatch).
 
-    When the reference ran the whole join, the result of the last TIMED step is compared; when it ran a prefix of the upstream
-    rows (bounded sample), the GPU re-runs exactly that prefix (uid_range) on its resident operands."""
+    The CPU leg scored the first `cpu_perms` permutations (they belong to the first permutation batch).  When the reference ran
+    the whole join, the result of the last TIMED step (first batch) is compared; when it ran a prefix of the upstream rows
+    (bounded sample), the GPU re-runs exactly that prefix (uid_range) on its resident operands."""
     from oracle import pyoracle as po  # the checker
 
     out = {"checked": True, "rule": "SURVEY App. A.7: f32 permutation maxima bit-exact, top-K score multiset bit-exact, entries above the K-th score identical",
-           "against": "the reference's own join (oracle/_ref) in the cpu_baseline leg of this run", "level4_pairs": 0, "mismatches": 0, "methods": {}}
+           "against": "the reference's own join (oracle/_ref) in the cpu_baseline leg of this run", "permutations_compared": int(cpu_perms),
+           "level4_pairs": 0, "mismatches": 0, "methods": {}}
     for method, r in ref_out.items():
         want = po.JoinedRes([po.Score(float(s[0]), int(s[1]), int(s[2]), int(s[3]), int(s[4])) for s in r["scores"]], np.asarray(r["perm"], dtype=np.float64))
         x = int(r["x"])
-        if x == lv4.n_uids and "4" in last_out[method][1]:
-            got, how = last_out[method][1]["4"], "whole join, result of the last timed step"
+        if x == lv4.n_uids and "4" in last_out[method][2]:
+            got, how = last_out[method][2]["4"], "whole join, result of the last timed step"
         else:
+            reset_masks(state[method])
             got, how = rerun_level4_prefix(state[method], lv4, w, x, api), f"first {x} upstream rows, re-run on the GPU with uid_range"
+        got = po.JoinedRes(got.scores, np.asarray(got.permuted_scores, dtype=np.float64)[:cpu_perms])
         try:
             po.compare_results(got, want, what=f"bench parity {method}")
             bad = 0
@@ -534,9 +553,14 @@ def main():
         return c.value
 
     # ---- resident state: one exec per method with table + masks + packed gene rows in HBM ----
+    # permutations beyond --perm-batch are scored as sequential batches through the same exec (masks of every batch resident)
+    batch_perms = int(min(w.n_perms, max(a.perm_batch, 1)))
+    n_batches = (w.n_perms + batch_perms - 1) // batch_perms
+    W1m = (n + 63) // 64
+    masks_dev = torch.from_numpy(np.ascontiguousarray(w.perm_masks).view(np.int64)).cuda() if n_batches > 1 else None
     state = {}
     for method in ("method1", "method2"):
-        ex = api.JoinExec(method, w.n_cases, w.n_ctrls, w.n_perms, device=local_rank)
+        ex = api.JoinExec(method, w.n_cases, w.n_ctrls, batch_perms, device=local_rank)
         ex.set_stream(stream.cuda_stream)
         ex.kernel = kernel
         ex.top_k = a.top_k
@@ -544,7 +568,7 @@ def main():
             ex.generateValueTable()
         else:
             ex.setValueTable(w.value_table)
-        ex.setPermutedMasks(w.perm_masks)
+        ex.setPermutedMasks(w.perm_masks[:batch_perms])
         d1 = ex.createPathSet(w.gene_bits.shape[0])
         d1.load_bits(w.gene_bits)
         d2 = ex.createPathSet(w.gene_bits2.shape[0])
@@ -552,18 +576,24 @@ def main():
         # the join indices are inputs like the gene rows: resident on the device for the `value` measurement
         uid = {k: api.UidRelSet(lv[k].path_length, lv[k].src, lv[k].trg, lv[k].count, lv[k].location, lv[k].signs).make_resident(ex) for k in names}
         state[method] = dict(ex=ex, d1=d1, d2=d2, uid=uid, perm_t=torch.zeros(ex.iterations, dtype=torch.float32, device="cuda"),
-                             perm_all=torch.zeros(ex.iterations * world, dtype=torch.float32, device="cuda"))
+                             perm_all=torch.zeros(world * n_batches * ex.iterations, dtype=torch.float32, device="cuda"))
 
-    def merge_last_level(st, results):
-        """The last level's one data-path collective (per-permutation maxima over NVLink) for a perm-sharded job."""
+    def export_block(st, b):
+        """This rank's maxima of batch b into its slot of the [rank][batch][Ip] result vector (device to device, on the exec's stream)."""
+        ex = st["ex"]
+        with torch.cuda.stream(st.get("stream", stream)):
+            if b == 0 and shard_perms:
+                st["perm_all"].zero_()
+            off = (rank * n_batches + b) * ex.iterations
+            _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_all"].data_ptr() + 4 * off, ex.iterations))
+
+    def merge_last_level(st, results=None):
+        """The one data-path collective of a perm-sharded job: every rank has dropped its maxima into its slots of a zeroed
+        [N][batches][Ip] vector and ONE NCCL allreduce(max) over NVLink merges them (maxima are >= +0, so max against the zeros
+        is concatenation)."""
         if not shard_perms:
             return
-        ex = st["ex"]
-        # result assembly: every rank drops its block of maxima into a zeroed N x I vector and ONE NCCL
-        # allreduce(max) over NVLink merges them (maxima are >= +0, so max against the zeros is concatenation)
         with torch.cuda.stream(st.get("stream", stream)):  # the stream the exec launches on
-            st["perm_all"].zero_()
-            _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_all"].data_ptr() + 4 * ex.iterations * rank, ex.iterations))
             dist.all_reduce(st["perm_all"], op=dist.ReduceOp.MAX)
 
     def schedule_resident(st, results, collective=True, single=False):
@@ -586,8 +616,9 @@ def main():
                 operand = results["_p3"]
             res_set = ex.createPathSet(lv[k].n_pairs) if (keep or (k in ("2", "3") and a.path_length > int(k))) else zero
             if k == last and shard_perms and not single:
-                r = ex.join(uid[k], prev, operand, res_set)
-                if collective:
+                r = ex.join(uid[k], prev, operand, res_set, skip_host_perm=n_batches > 1)
+                export_block(st, st.get("batch", 0))
+                if collective and st.get("batch", 0) == n_batches - 1:
                     merge_last_level(st, results)
             elif k == last and world > 1 and not single:
                 r = ex.join(uid[k], prev, operand, zero, uid_range=my_shard, skip_host_perm=True)
@@ -606,14 +637,37 @@ def main():
                 prev = res_set
         return info
 
+    def run_batches(st, collective=True, single=False):
+        """All permutation batches of one method; returns (per-level info with kernel times summed over the batches, results of the
+        last batch, results of batch 0)."""
+        info_sum, res_last, res_first = None, None, None
+        for b in range(n_batches):
+            ex = st["ex"]
+            st["batch"] = b
+            if n_batches > 1:
+                nb = min(batch_perms, w.n_perms - b * batch_perms)
+                ex.setPermutedMasksDevice(masks_dev.data_ptr() + 8 * b * batch_perms * W1m, nb)
+            res = {}
+            info = schedule_resident(st, res, collective=collective, single=single)
+            if n_batches > 1 and not shard_perms:
+                export_block(st, b)
+            for k in [k for k in res if k.startswith("_")]:
+                del res[k]  # kept path sets go back to the block cache now, not when the next step overwrites `last_out`
+            if info_sum is None:
+                info_sum, res_first = info, res
+            else:
+                for k in info:
+                    info_sum[k]["kernel_ms"] += info[k]["kernel_ms"]
+                    info_sum[k]["exact_units"] += info[k].get("exact_units", 0)
+                    info_sum[k]["total_units"] += info[k].get("total_units", 0)
+            res_last = res
+        st["batch"] = 0
+        return info_sum, res_last, res_first
+
     def step_resident():
         out = {}
         for method in ("method1", "method2"):
-            res = {}
-            info = schedule_resident(state[method], res)
-            for k in [k for k in res if k.startswith("_")]:
-                del res[k]  # kept path sets go back to the block cache now, not when the next step overwrites `last_out`
-            out[method] = (info, res)
+            out[method] = run_batches(state[method])
         return out
 
     def sync_all():
@@ -676,15 +730,18 @@ def main():
             if shard_perms:
                 # rank r recomputes, alone, the block of permutations rank (r + 1) % N scored, and compares it bit for bit with
                 # that block of the all-reduced N x I vector; the top-K (permutation independent) must be the same on every rank
+                # (with several permutation batches: the neighbour's first batch)
                 blk = (rank + 1) % world
                 all_red = st["perm_all"].cpu().numpy().astype(np.float64)
-                ex.setPermutedMasks(synth.make_perm_masks(w.n_cases, w.n_ctrls, w.n_perms, a.seed + 3 + 1000 * blk))
+                ex.setPermutedMasks(synth.make_perm_masks(w.n_cases, w.n_ctrls, w.n_perms, a.seed + 3 + 1000 * blk)[:batch_perms])
                 res = {}
+                st["batch"] = 0
                 schedule_resident(st, res, collective=False, single=True)
                 mine = res[last]
-                bad += int(not np.array_equal(mine.permuted_scores.view(np.uint64), all_red[blk * ex.iterations: blk * ex.iterations + w.n_perms].view(np.uint64)))
+                o0 = blk * n_batches * ex.iterations
+                bad += int(not np.array_equal(mine.permuted_scores.view(np.uint64), all_red[o0: o0 + batch_perms].view(np.uint64)))
                 bad += int([(s_.score, s_.src, s_.trg, s_.cases, s_.ctrls) for s_ in mine.scores] != [(s_.score, s_.src, s_.trg, s_.cases, s_.ctrls) for s_ in merged.scores])
-                ex.setPermutedMasks(w.perm_masks)
+                ex.setPermutedMasks(w.perm_masks[:batch_perms])
                 del res
             else:
                 # every rank recomputes the whole last-level join and compares it with the merged shards
@@ -763,14 +820,17 @@ def main():
             for k in names:
                 inf = last_out[method][0][k]
                 kms = float(inf["kernel_ms"])
-                per_level[method][k] = {"pairs": int(inf["pairs"]), "kernel_ms": kms, "kernel": {1: "dense", 2: "sparse"}.get(inf["kernel"], "none") + ("+precount" if inf.get("precounted") else "") + ("+split-carrier" if inf.get("split_carrier") else ""),
+                per_level[method][k] = {"pairs": int(inf["pairs"]), "kernel_ms": kms, "kernel": {1: "dense", 2: "sparse"}.get(inf["kernel"], "none") + ("+precount" if inf.get("precounted") else "") + ("+split-carrier" if inf.get("split_carrier") else "") + ("+screened" if inf.get("screened") else ""),
+                                        "exact_fraction": (inf["exact_units"] / inf["total_units"]) if inf.get("screened") and inf.get("total_units") else None,
                                         "pair_perm_per_s": (inf["pairs"] * w.n_perms / (kms * 1e-3)) if kms > 0 else None}
 
     # ---- end-to-end through the reference-facing calls with HOST buffers (R-facing int matrices), N GPUs ----
     e2e = None
     if not a.no_e2e and w.value_table is None:
         sys.stderr.write("[bench] e2e skipped: no host value table at this size (generated on the device)\n")
-    if not a.no_e2e and w.value_table is not None:
+    if not a.no_e2e and w.value_table is not None and n_batches > 1:
+        sys.stderr.write("[bench] e2e skipped: several permutation batches (the int permutation matrix would not fit the host)\n")
+    if not a.no_e2e and w.value_table is not None and n_batches == 1:
         data1_i = torch.from_numpy(synth.unpack_bits(w.gene_bits, n)).pin_memory().numpy()
         data2_i = torch.from_numpy(synth.unpack_bits(w.gene_bits2, n)).pin_memory().numpy()
         bits = np.unpackbits(w.perm_masks.view(np.uint8), axis=1, bitorder="little")[:, :n].astype(bool)
@@ -946,12 +1006,16 @@ def main():
     #      the GPU's level-4 result of the last timed step (SURVEY App. A.7 rule: f32 maxima bit for bit, the multiset of top-K
     #      scores, every entry above the K-th score; entries tied with the K-th score only need to carry that score) ----
     cpu, parity = None, None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and w.value_table is None and (w.n_cases + 1) * (w.n_ctrls + 1) * 8 <= (8 << 30):
+        # the table was generated on the device (no host generator finishes at this size): the CPU leg gets a copy of it
+        w.value_table = state["method1"]["ex"].getValueTable()
     if rank == 0 and world == 1 and not a.no_cpu_baseline and w.value_table is not None and a.path_length >= 4:
         arm = None
         try:
             arm = ReferenceArm(w, a)
             cpu, ref_out = arm.sample(a.cpu_seconds, results=True)
-            parity = check_parity(ref_out, last_out, state, lv["4"], w, api)
+            parity = check_parity(ref_out, last_out, state, lv["4"], w, api, cpu_perm_count(w, a),
+                                  lambda st: st["ex"].setPermutedMasks(w.perm_masks[:batch_perms]))
         except AssertionError:
             raise
         except Exception as e:  # the GPU numbers stand on their own

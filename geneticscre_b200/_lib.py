@@ -56,6 +56,7 @@ SYMBOLS = {
     "gcre_exec_get_value_table": (_I, [_VP, C.POINTER(C.c_double), _I, _I]),
     "gcre_exec_set_permuted_cases_i32": (_I, [_VP, C.POINTER(C.c_int32), _I, _I]),
     "gcre_exec_set_permuted_masks_u64": (_I, [_VP, C.POINTER(C.c_uint64), _I]),
+    "gcre_exec_set_permuted_masks_device": (_I, [_VP, _VP, _I]),
     "gcre_pathset_create": (_I, [_VP, _U32, C.POINTER(_VP)]),
     "gcre_pathset_destroy": (_I, [_VP]),
     "gcre_pathset_size": (_I, [_VP, C.POINTER(_U32)]),

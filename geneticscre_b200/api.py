@@ -216,6 +216,10 @@ class JoinExec:
             raise ValueError("masks must be uint64[n_perms][ceil(n/64)]")
         check(self._lib.gcre_exec_set_permuted_masks_u64(self._h, _ptr(m, C.c_uint64), m.shape[0]))
 
+    def setPermutedMasksDevice(self, device_ptr, n_perms):
+        """Packed masks uint64[n_perms][ceil(n/64)] already in this GPU's memory; ordered on the exec's stream (extension)."""
+        check(self._lib.gcre_exec_set_permuted_masks_device(self._h, C.c_void_p(int(device_ptr)), int(n_perms)))
+
     def createPathSet(self, size):
         out = C.c_void_p()
         check(self._lib.gcre_pathset_create(self._h, int(size), C.byref(out)))

@@ -311,6 +311,8 @@ static void unpool_event(int device, bool timing, cudaEvent_t ev) {
 struct gcre_pathset;
 struct gcre_uidset;
 
+constexpr unsigned kSpecCand = 1024;  // candidates copied to the host speculatively with the scalars (a 12 M-pair join appends ~300)
+
 struct gcre_exec {
   int M = 1, n_cases = 0, n_ctrls = 0, n = 0, W64 = 0, Wp = 0, iters = 0, Ip = 0, Iw = 0, device = 0, sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -348,6 +350,10 @@ struct gcre_exec {
                                   // [4] seed entries, [5] retry entries of a screened join, [6..7] work counter of its exact passes
   DevBuf cand, scratch, scan_tmp, retry, seed;
   unsigned* h_scalars = nullptr;  // pinned
+  // page-locked landing area of a join's results: [kSpecCand candidates][Ip permutation maxima].  They are copied behind every
+  // launch together with the scalars, so a join waits for the device once instead of three times.
+  PinnedBlock h_res{nullptr, 0};
+  bool h_perm_fresh = false;      // h_res holds the maxima of the last launch of the last join
   // path sets and join indices created from this exec: gcre_exec_destroy frees their device memory and orphans them (ex =
   // nullptr), so destroying the exec first is legal and a later gcre_pathset_destroy only deletes the host object
   mutable std::mutex child_mu;
@@ -552,6 +558,7 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
   ex->scratch.release();
   // streams (drained above), events and the page-locked words go back to the process-wide pools
   unpool_pinned(ex->h_scalars);
+  pinned_big_release(ex->h_res);
   unpool_event(ex->device, true, ex->ev0);
   unpool_event(ex->device, true, ex->ev1);
   unpool_event(ex->device, false, ex->ev_piece);
@@ -855,6 +862,24 @@ extern "C" int gcre_exec_set_permuted_masks_u64(gcre_exec* ex, const uint64_t* m
   return GCRE_OK;
 }
 
+// The same from a buffer in this exec's device memory (permutation batches that stay resident; multi-GPU fan-out).  Ordered on
+// the exec's stream; no host wait.
+extern "C" int gcre_exec_set_permuted_masks_device(gcre_exec* ex, const uint64_t* d_masks, int n_perms) {
+  if (!ex || (!d_masks && n_perms > 0)) return fail(GCRE_ERR_ARG, "null argument");
+  CKS(use_device(ex));
+  if (ex->iters > 0 && n_perms <= 0) return fail(GCRE_ERR_ASSERT, "assertion");
+  const int have = std::min(n_perms, ex->iters);
+  CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)ex->iters * ex->W64, 1) * 8, ex->stream));
+  if (have > 0) CK(cudaMemcpyAsync(ex->d_masks, d_masks, (size_t)have * ex->W64 * 8, cudaMemcpyDeviceToDevice, ex->stream));
+  if (have < ex->iters) {
+    cycle_perm_rows_kernel<<<grid_for((long long)(ex->iters - have) * ex->W64, 256), 256, 0, ex->stream>>>(ex->d_masks, have, ex->iters, ex->W64);
+    CK(cudaGetLastError());
+    LAUNCHED();
+  }
+  CKS(rebuild_mask_layouts(ex));
+  return GCRE_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // path sets
 // ------------------------------------------------------------------------------------------------------------------
@@ -1101,7 +1126,12 @@ extern "C" int gcre_pathset_select(const gcre_pathset* ps, const int32_t* indice
                                                                                        row_vec, (ulonglong2*)res->d_rows);
       CK(cudaGetLastError());
       LAUNCHED();
-      CK(cudaStreamSynchronize(ex->stream));
+      // no host wait: the copy above has read `indices` when it returns unless they are page-locked - then wait for it
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, indices) != cudaSuccess || attr.type != cudaMemoryTypeUnregistered) {
+        cudaGetLastError();
+        CK(cudaStreamSynchronize(ex->stream));
+      }
       return GCRE_OK;
     }();
     if (rc != GCRE_OK) {
@@ -1600,8 +1630,41 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
 
   // ---- kernel choice ----
   int kernel = opts ? opts->kernel : GCRE_KERNEL_AUTO;
-  if (kernel != GCRE_KERNEL_DENSE && kernel != GCRE_KERNEL_SPARSE)
-    kernel = (sparse_supported(ex->n, t_needed, ex->Iw) && sparse_preferred(ex->W64, ex->Ip, ex->Iw)) ? GCRE_KERNEL_SPARSE : GCRE_KERNEL_DENSE;
+  if (kernel != GCRE_KERNEL_DENSE && kernel != GCRE_KERNEL_SPARSE) {
+    kernel = GCRE_KERNEL_DENSE;
+    if (sparse_supported(ex->n, t_needed, ex->Iw)) {
+      const int npb = ex->Iw / 32;
+      const double dense_ns = dense_pair_ns(ex->W64, ex->Ip, ex->M);
+      if (sparse_pair_ns(npb, ex->M, (double)mp1 * ex->M) <= dense_ns) {
+        kernel = GCRE_KERNEL_SPARSE;  // wins even if every partner added its densest half-row in full
+      } else if (sparse_pair_ns(npb, ex->M, 0.0) < dense_ns && pair_hi > pair_lo) {
+        // it depends on the rows: carriers a partner adds to its upstream row, averaged over 2,048 pairs spread over the join
+        JoinParams q;
+        memset(&q, 0, sizeof q);
+        q.p0 = paths0->d_rows;
+        q.p1 = paths1->d_rows;
+        q.Wp = ex->Wp;
+        q.prefix = (const unsigned long long*)us->prefix.p;
+        q.location = (const uint32_t*)us->loc.p;
+        q.n_uids = n_uids;
+        q.signs = (const int32_t*)us->signs.p;
+        q.path_length = path_length;
+        const int n_samples = (int)std::min<unsigned long long>(2048, pair_hi - pair_lo);
+        unsigned long long* d_sums = reinterpret_cast<unsigned long long*>(ex->d_scalars + 8);
+        CK(cudaMemsetAsync(d_sums, 0, 2 * sizeof(unsigned long long), ex->stream));
+        if (ex->M == 1) sample_overlap_kernel<1><<<grid_for((long long)n_samples * 32, 256), 256, 0, ex->stream>>>(q, pair_lo, pair_hi, n_samples, d_sums);
+        else sample_overlap_kernel<2><<<grid_for((long long)n_samples * 32, 256), 256, 0, ex->stream>>>(q, pair_lo, pair_hi, n_samples, d_sums);
+        CK(cudaGetLastError());
+        LAUNCHED();
+        CK(cudaMemcpyAsync(ex->h_scalars + 8, d_sums, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ex->stream));
+        CK(cudaStreamSynchronize(ex->stream));
+        unsigned long long sums[2];
+        memcpy(sums, ex->h_scalars + 8, sizeof sums);
+        const double new_per_pair = (double)sums[1] / n_samples;
+        if (sparse_pair_ns(npb, ex->M, new_per_pair) <= dense_ns) kernel = GCRE_KERNEL_SPARSE;
+      }
+    }
+  }
   // an explicit request for the sparse kernel is honoured whenever its index widths allow
   if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, ex->Iw)) kernel = GCRE_KERNEL_DENSE;
   SparseParams sp;
@@ -1751,6 +1814,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     plan.push_back({item_lo, item_lo + prefix_items, true});
     plan.push_back({item_lo + prefix_items, item_hi, false});
   }
+  ex->h_perm_fresh = false;
   std::vector<gcre_score> held;
   std::vector<Cand> h_cand;
   unsigned long long thr_key = score_key(-std::numeric_limits<double>::infinity());
@@ -1827,7 +1891,13 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     }
     CK(cudaEventRecord(ex->ev1, ex->stream));
     CK(cudaMemcpyAsync(ex->h_scalars, ex->d_scalars, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, ex->stream));
+    if (!ex->h_res.p) CK(pinned_big_acquire((size_t)kSpecCand * sizeof(Cand) + (size_t)ex->Ip * 4, &ex->h_res));
+    Cand* h_spec = static_cast<Cand*>(ex->h_res.p);
+    const unsigned n_spec = std::min(cap, kSpecCand);
+    CK(cudaMemcpyAsync(h_spec, ex->cand.p, (size_t)n_spec * sizeof(Cand), cudaMemcpyDeviceToHost, ex->stream));
+    CK(cudaMemcpyAsync(h_spec + kSpecCand, ex->d_perm_max, (size_t)ex->Ip * 4, cudaMemcpyDeviceToHost, ex->stream));
     CK(cudaStreamSynchronize(ex->stream));
+    ex->h_perm_fresh = true;
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ex->ev0, ex->ev1));
     kernel_ms += ms;
@@ -1854,8 +1924,12 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     }
     if (n_cand) {
       h_cand.resize(n_cand);
-      CK(cudaMemcpyAsync(h_cand.data(), ex->cand.p, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, ex->stream));
-      CK(cudaStreamSynchronize(ex->stream));
+      if (n_cand <= n_spec) {
+        memcpy(h_cand.data(), h_spec, (size_t)n_cand * sizeof(Cand));  // already here
+      } else {
+        CK(cudaMemcpyAsync(h_cand.data(), ex->cand.p, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, ex->stream));
+        CK(cudaStreamSynchronize(ex->stream));
+      }
       for (unsigned k = 0; k < n_cand; k++) {
         gcre_score sc;
         sc.score = key_score(h_cand[k].key);
@@ -1887,7 +1961,14 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   }
 
   CKS(emit_topk(held, top_k, out_scores, n_scores));
-  if (out_perm && !(opts && opts->skip_host_perm)) CKS(gcre_exec_read_perm_max(ex, out_perm));
+  if (out_perm && !(opts && opts->skip_host_perm)) {
+    if (ex->h_perm_fresh && launches > 0) {  // the maxima came back with the last launch's scalars
+      const float* hp = reinterpret_cast<const float*>(static_cast<Cand*>(ex->h_res.p) + kSpecCand);
+      for (int r = 0; r < ex->iters; r++) out_perm[r] = (double)hp[r];  // src/join_base.cpp:145-146
+    } else {
+      CKS(gcre_exec_read_perm_max(ex, out_perm));
+    }
+  }
   tr.mark("results");
   tr.done(keep ? "join(keep)" : "join");
   if (opts) {
@@ -1924,6 +2005,7 @@ extern "C" int gcre_exec_import_perm_max(gcre_exec* ex, const void* device_src, 
   if (count < 0 || count > ex->Ip) return fail(GCRE_ERR_RANGE, "assertion");
   CKS(use_device(ex));
   CK(cudaMemcpyAsync(ex->d_perm_max, device_src, (size_t)count * 4, cudaMemcpyDeviceToDevice, ex->stream));
+  ex->h_perm_fresh = false;
   return GCRE_OK;
 }
 

@@ -683,12 +683,18 @@ static inline bool sparse_supported(int n, long long t_needed, int Iw) {
   return t_needed <= 65535 && ((unsigned long long)n + 1) * (unsigned long long)Iw < 0xffffffffull;
 }
 
-// AUTO choice.  Per pair the dense kernel issues ~ W64 * Ip * 5 / 32 warp instructions (Ip = permutations padded to its
-// 128-wide tile), the sparse kernel ~1,000 per 1,024-permutation block almost independent of W64 (measured on config 3:
-// 950 / pair, profiles/r1_sparse_m1_level4_full.txt).  Dense wins only for very short rows with few permutations
-// (the vignette: W64 = 4).  Measured at 50,000 patients / 100 permutations: dense 1.9 s per step.
-static inline bool sparse_preferred(int W64, int Ip_dense, int Iw) {
-  return (long long)W64 * Ip_dense > 6400ll * (Iw / 32);
+// AUTO choice: a cost model in nanoseconds per pair, calibrated on B200 (profiles/r2_density_sweep.json).
+//   dense : every pair pays W64 * Ip * M word-ops (Ip = permutations padded to the 128-wide tile) at the measured 2.1e12 word-ops/s
+//           of the POPC pipe, whatever the rows hold;
+//   sparse: a fixed part per pair and 1,024-permutation block (filter pass, flush, look-ups) plus a part proportional to the
+//           carriers the partner ADDS to the upstream row (gathers + carry-save adds).
+// The sparse walk wins for rare-variant rows at any cohort size; the dense kernel wins for very short rows (the vignette:
+// W64 = 4) and when partner rows add thousands of carriers (common variants: GWASPA(threshold = 0.5)).  The carriers added per
+// pair are bounded by the densest partner half-row; when that bound does not decide, a 2,048-pair sample (sample_overlap_kernel)
+// measures them.
+static inline double dense_pair_ns(int W64, int Ip_dense, int M) { return (double)W64 * Ip_dense * M / 2100.0; }
+static inline double sparse_pair_ns(int n_perm_blocks, int M, double new_carriers_per_pair) {
+  return n_perm_blocks * ((M == 1 ? 0.55 : 1.0) + 0.011 * new_carriers_per_pair);
 }
 
 template <int M, bool KEEP, bool PC>

@@ -67,7 +67,8 @@ typedef struct {
 
 /* which kernel family a join may use */
 typedef enum {
-  GCRE_KERNEL_AUTO = 0,   /* pick by operand density */
+  GCRE_KERNEL_AUTO = 0,   /* pick by row length, permutation count and operand density (cost model in join_sparse.cuh; the carriers a
+                             partner adds per pair are bounded by the densest row or, when that does not decide, sampled) */
   GCRE_KERNEL_DENSE = 1,  /* AND + POPC against word-major permutation mask tiles */
   GCRE_KERNEL_SPARSE = 2  /* carrier-list walk over patient-major permutation masks (bit-sliced counters) */
 } gcre_kernel;
@@ -139,6 +140,9 @@ int gcre_exec_set_permuted_cases_i32(gcre_exec* ex, const int32_t* perm, int row
 /* Same masks already packed: uint64[n_perms][ceil(n/64)], bit c of row r set iff patient c is a case under
  * permutation r (what setPermutedCases computes, without the 32x larger int matrix). */
 int gcre_exec_set_permuted_masks_u64(gcre_exec* ex, const uint64_t* masks, int n_perms);
+/* The same from a buffer in this exec's device memory (e.g. one batch of a resident set of permutations); ordered on the
+ * exec's stream, returns without waiting. */
+int gcre_exec_set_permuted_masks_device(gcre_exec* ex, const uint64_t* d_masks, int n_perms);
 
 /* JoinExec::createPathSet(size)  (src/join_base.cpp:156-161): size rows of width_ul*method words, zero-filled. */
 int gcre_pathset_create(const gcre_exec* ex, uint32_t size, gcre_pathset** out);
