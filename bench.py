@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--table", default="auto", choices=["auto", "host", "device"],
                     help="value table: numpy on the host and uploaded (what R does), or generated on the device (needed for n >= 50k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the fixed-work (row-sharded) measurement reported as `strong`")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=2, choices=[1, 2],
                     help="e2e leg: 2 = submit the two methods from two host threads (uploads of one overlap joins of the other); 1 = sequential")
@@ -174,7 +175,7 @@ class ClockSampler:
 # SUBPROCESSES that are replaced after a bounded number of joins (round 1's in-process arm was OOM-killed on the 1-GPU box).
 # The workers load only oracle/_ref/*.so; the process that owns the GPU never maps the reference, and the reference arm never
 # maps the CUDA engine.
-REF_JOINS_PER_WORKER = {"method1": 64, "method2": 2}
+REF_JOINS_PER_WORKER = {"method1": 64, "method2": 6}  # method 2: upper limit, lowered to what the RAM allows
 
 
 def mem_available_bytes():
@@ -543,6 +544,18 @@ def main():
     last = names[-1]
     shards = gdist.shard_bounds(lv[last].count, world)
     my_shard = shards[rank]
+    # Fixed-work decomposition at path length 4: the level-4 shard of a rank is a contiguous range of paths3 rows, so the rank
+    # builds ONLY those rows at level 3 (a contiguous range of level-3 upstream rows, cut where a level-3 row's results end);
+    # ranges are balanced by level-4 pairs plus the level-3 pairs they cost (a KEEP pair ~ 4 score-only pairs).
+    l3_shard = l4_rows = None
+    if a.path_length == 4 and world > 1:
+        c3 = lv["3"].count.astype(np.int64)
+        pidx3 = np.concatenate([[0], np.cumsum(c3)])
+        cs4 = np.concatenate([[0], np.cumsum(lv["4"].count.astype(np.int64))])
+        weight = cs4[pidx3[1:]] - cs4[pidx3[:-1]] + 4 * c3
+        l3_shard = gdist.shard_bounds(weight, world)[rank]
+        l4_rows = (int(pidx3[l3_shard[0]]), int(pidx3[l3_shard[1]]))
+    default_mode = "perms" if shard_perms else ("rows" if world > 1 else "single")
     stream = torch.cuda.current_stream()
 
     def launches():
@@ -596,9 +609,11 @@ def main():
         with torch.cuda.stream(st.get("stream", stream)):  # the stream the exec launches on
             dist.all_reduce(st["perm_all"], op=dist.ReduceOp.MAX)
 
-    def schedule_resident(st, results, collective=True, single=False):
+    def schedule_resident(st, results, collective=True, single=False, mode=None):
         """Levels 1a,1b,2,3,(4,5) with device-resident inputs; the last level is sharded across ranks
-        (`single`: this rank alone does the whole job - the cross-check of the multi-GPU result)."""
+        (`single`: this rank alone does the whole job - the cross-check of the multi-GPU result).
+        mode: "perms" (own permutation block, all pairs), "rows" (fixed work: upstream rows sharded), "single"."""
+        mode = "single" if single else (mode or default_mode)
         ex, d1, d2, uid = st["ex"], st["d1"], st["d2"], st["uid"]
         zero = ex.createPathSet(0)
         info = {}
@@ -615,13 +630,16 @@ def main():
             else:
                 operand = results["_p3"]
             res_set = ex.createPathSet(lv[k].n_pairs) if (keep or (k in ("2", "3") and a.path_length > int(k))) else zero
-            if k == last and shard_perms and not single:
+            if k == last and mode == "perms":
                 r = ex.join(uid[k], prev, operand, res_set, skip_host_perm=n_batches > 1)
                 export_block(st, st.get("batch", 0))
                 if collective and st.get("batch", 0) == n_batches - 1:
                     merge_last_level(st, results)
-            elif k == last and world > 1 and not single:
-                r = ex.join(uid[k], prev, operand, zero, uid_range=my_shard, skip_host_perm=True)
+            elif k == "3" and mode == "rows" and l3_shard is not None:
+                # this rank's slice of level 3: exactly the paths3 rows its level-4 shard reads
+                r = ex.join(uid[k], prev, operand, res_set, uid_range=l3_shard)
+            elif k == last and mode == "rows":
+                r = ex.join(uid[k], prev, operand, zero, uid_range=(l4_rows if l4_rows is not None else my_shard), skip_host_perm=True)
                 _lib.check(lib.gcre_exec_export_perm_max(ex._h, st["perm_t"].data_ptr(), ex.iterations))
                 # ONE data-path collective per join: NCCL allreduce(max) of the f32 maxima (+ a K-entry gather)
                 gdist.merge_shard_result(r, a.top_k, api.merge_topk, api.Score, dist, device_perm=st["perm_t"], n_perms=w.n_perms)
@@ -762,6 +780,45 @@ def main():
                                  "every rank recomputed the whole last-level join alone and compared maxima (bit for bit) and top-K with the merged shards")}
         if multi_parity["mismatches"]:
             raise AssertionError(f"multi-GPU result differs from the single-rank recomputation: {multi_parity}")
+
+    # ---- N > 1: the same FIXED job (rank 0's permutations, first batch) row-sharded over the N GPUs vs done by one GPU alone ----
+    strong = None
+    if world > 1 and not a.no_strong and last_out is not None:
+        block0 = synth.make_perm_masks(w.n_cases, w.n_ctrls, w.n_perms, a.seed + 3)[:batch_perms] if rank > 0 else w.perm_masks[:batch_perms]
+        for st in state.values():
+            st["ex"].setPermutedMasks(block0)
+            st["batch"] = 0
+
+        def timed(mode, steps):
+            def one():
+                for method in ("method1", "method2"):
+                    res = {}
+                    schedule_resident(state[method], res, mode=mode)
+                    del res
+            for _ in range(2):
+                one()
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                one()
+            e1.record(stream)
+            sync_all()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        k_steps = max(3, min(a.steps, 10))
+        ms_one = timed("single", k_steps)
+        ms_rows = timed("rows", k_steps)
+        strong = {"job": f"the N=1 job ({batch_perms} permutations, all pairs, methods 1+2) done once by the {world} GPUs together",
+                  "decomposition": ("level-4 upstream rows sharded by pair count; each rank builds only its own paths3 rows at level 3; levels 1a/1b/2 replicated; "
+                                    "one NCCL allreduce(max) + top-K gather per method" if l3_shard is not None else
+                                    "last level's upstream rows sharded by pair count, earlier levels replicated; one NCCL allreduce(max) + top-K gather per method"),
+                  "ms_per_step_one_gpu": ms_one, "ms_per_step": ms_rows, "speedup": ms_one / ms_rows, "efficiency": ms_one / ms_rows / world, "steps": k_steps,
+                  "timing": "CUDA events on the launching stream, max over ranks"}
+        for st in state.values():
+            st["ex"].setPermutedMasks(w.perm_masks[:batch_perms])
 
     # ---- roofline of the dominant kernel: the last-level join of each method, timed live by CUDA events inside join ----
     roof = None
@@ -1029,7 +1086,7 @@ def main():
         line = {"metric": "path-pair*perm scores/s", "value": value, "unit": "pair*perm/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (shard_perms or world == 1) else "strong", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,
-                "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "multi_gpu_parity": multi_parity, "per_level": per_level,
+                "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "multi_gpu_parity": multi_parity, "strong": strong, "per_level": per_level,
                 "pair_perm_per_step": pp_step, "workload_gen_s": round(gen_s, 1)}
         emit_line(line)
     if world > 1:

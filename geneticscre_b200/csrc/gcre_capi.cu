@@ -1613,9 +1613,18 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   CKS(materialize_zero(const_cast<gcre_pathset*>(paths0)));
   CKS(materialize_zero(const_cast<gcre_pathset*>(paths1)));
   if (keep) {
-    // a full join whose result rows are the running sums of the counts overwrites every word of the result set
-    if (pair_lo == 0 && pair_hi == total && us->res_is_prefix) paths_res->zero_pending = false;
-    else CKS(materialize_zero(paths_res));
+    // result rows that are the running sums of the counts: the join overwrites every word of rows [pair_lo, pair_hi); only the
+    // rest of a fresh set needs its zeros (nothing for a full join)
+    if (us->res_is_prefix) {
+      if (paths_res->zero_pending) {
+        const size_t rb = row_words(ex) * 8;
+        if (pair_lo > 0) CK(cudaMemsetAsync(paths_res->d_rows, 0, (size_t)pair_lo * rb, ex->stream));
+        if (pair_hi < total) CK(cudaMemsetAsync(paths_res->d_rows + (size_t)pair_hi * row_words(ex), 0, (size_t)(total - pair_hi) * rb, ex->stream));
+        paths_res->zero_pending = false;
+      }
+    } else {
+      CKS(materialize_zero(paths_res));
+    }
   }
 
   tr.mark("checks");
@@ -1673,7 +1682,8 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   if (kernel == GCRE_KERNEL_SPARSE) {
     CKS(ensure_patient_major(ex));
     // upstream operand: rows that came out of a KEEP join carry their counts and totals - no carrier lists needed
-    const bool base_emitted = paths0->view.pcnt && paths0->view.pcnt_gen == ex->mask_gen && paths0->view.stats_valid && paths0 != paths_res;
+    const bool base_emitted = paths0->view.pcnt && paths0->view.pcnt_gen == ex->mask_gen && paths0->view.stats_valid && paths0 != paths_res &&
+                              ub >= paths0->view.emit_lo && ue <= paths0->view.emit_hi;
     if (!base_emitted) CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths0)));
     CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths1)));
     sp.off0 = paths0->view.off; sp.len0 = paths0->view.len; sp.car0 = paths0->view.car; sp.ncase0 = paths0->view.ncase;
@@ -1686,20 +1696,23 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     sp.n_perm_blocks = ex->Iw / 32;
     size_t budget = (size_t)24 << 30;  // device bytes a table of per-permutation counts may take (GCRE_PRECOUNT_MAX_MB overrides)
     if (const char* mb = std::getenv("GCRE_PRECOUNT_MAX_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
-    // kept rows take their counts along (join_sparse.cuh) when the join writes ALL of them (every result row is written only
-    // when path_idx is the running sum of the counts: res_is_prefix); GCRE_TEST_EMIT=0 (test hook) turns it off
+    // kept rows take their counts along (join_sparse.cuh) when result rows are the running sums of the counts (res_is_prefix:
+    // rows [pair_lo, pair_hi) are exactly the ones this call writes); GCRE_TEST_EMIT=0 (test hook) turns it off
     const char* emit_env = std::getenv("GCRE_TEST_EMIT");
     // <= 512 permutations: the split-carrier kernel (join_sparse_sc.cuh) runs instead and neither writes nor reads count tables
     const bool few_perms = sparse_sc_enabled(ex->Ip, sp.n_perm_blocks);
-    const bool emit = !few_perms && keep && pair_lo == 0 && pair_hi == total && us->res_is_prefix && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
+    const bool emit = !few_perms && keep && pair_hi > pair_lo && us->res_is_prefix && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
                       (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
     int pc_mode = emit ? PRECOUNT_NO : precount_mode(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget);
     if (few_perms && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;  // the split-carrier kernel is the better form there
     // Range-bound screening (join_screen.cuh): score-only joins whose upstream rows carry their counts AND count ranges.
-    // GCRE_SCREEN=0 turns it off; GCRE_TEST_SCREEN=1 (test hook) runs it on joins of any size.
+    // Opt-in (GCRE_SCREEN=1): measured on BASELINE config 3 the screening pass costs as much as the exact kernel it replaces
+    // (gathers and the filter dominate a pair, not the look-ups it saves) - profiles/r2_bench_screen_ab.txt.
+    // GCRE_TEST_SCREEN=1 (test hook) runs it on joins of any size.
     {
       const char* scr = std::getenv("GCRE_SCREEN");
-      screen_on = !keep && base_emitted && paths0->view.prange && !few_perms && pc_mode != PRECOUNT_YES && !(scr && *scr == '0');
+      const bool want = (scr && *scr == '1') || std::getenv("GCRE_TEST_SCREEN") != nullptr;
+      screen_on = want && !keep && base_emitted && paths0->view.prange && !few_perms && pc_mode != PRECOUNT_YES;
       if (screen_on && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;
     }
     if (pc_mode == PRECOUNT_SAMPLE) {
@@ -1951,10 +1964,13 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   }
   tr.mark("launches");
   if (keep) {
-    paths_res->max_half_pop = (pair_lo == 0 && pair_hi == total) ? (long long)ex->h_scalars[1] : -1;
+    // (rows outside a shard of a fresh result set are zero: the kernel's maximum over the written rows is the set's)
+    paths_res->max_half_pop = ((pair_lo == 0 && pair_hi == total) || us->res_is_prefix) ? std::max<long long>(paths_res->max_half_pop, (long long)ex->h_scalars[1]) : -1;
     if (sp.pcnt_res) {  // emitted with the rows
       paths_res->view.pcnt_gen = ex->mask_gen;
       paths_res->view.stats_valid = true;
+      paths_res->view.emit_lo = pair_lo;
+      paths_res->view.emit_hi = pair_hi;
     } else {
       drop_view(paths_res);
     }

@@ -78,6 +78,9 @@ struct SparseView {
   unsigned long long pcnt_gen = 0;  // exec->mask_gen the table was built for
   // min | max << 16 over the 32 permutations of every lane of the emitted counts: [item][perm block][lane] (join_screen.cuh)
   uint32_t* prange = nullptr;
+  // rows whose counts / ranges / len / ncase were emitted: a KEEP join over a shard of its upstream rows (multi-GPU: each
+  // rank builds only the rows its shard of the next level consumes) fills [emit_lo, emit_hi) only
+  unsigned long long emit_lo = 0, emit_hi = 0;
 };
 
 struct SparseParams {
@@ -693,8 +696,10 @@ static inline bool sparse_supported(int n, long long t_needed, int Iw) {
 // pair are bounded by the densest partner half-row; when that bound does not decide, a 2,048-pair sample (sample_overlap_kernel)
 // measures them.
 static inline double dense_pair_ns(int W64, int Ip_dense, int M) { return (double)W64 * Ip_dense * M / 2100.0; }
+// (density sweep at n = 10,000, 425 k pairs, 1,000 permutations: dense 77 ns per pair whatever the rows hold; sparse 3.5 / 7.3 / 20 /
+// 41 ns at ~22 / 80 / 260 / 570 carriers added per pair - method 2 about a third more)
 static inline double sparse_pair_ns(int n_perm_blocks, int M, double new_carriers_per_pair) {
-  return n_perm_blocks * ((M == 1 ? 0.55 : 1.0) + 0.011 * new_carriers_per_pair);
+  return n_perm_blocks * ((M == 1 ? 1.5 : 2.0) + (M == 1 ? 0.075 : 0.1) * new_carriers_per_pair);
 }
 
 template <int M, bool KEEP, bool PC>

@@ -325,7 +325,7 @@ def test_sharded_join_merges_to_full(engine, oracles, method, kernel):
 def test_pathset_row_access(engine):
     ex = engine.JoinExec("method2", 40, 37, 1)
     ps = ex.createPathSet(3)
-    row = np.arange(4, dtype=np.uint64) + np.uint64(1 << 40)
+    row = np.arange(4, dtype=np.uint64) + np.uint64(1 << 12)  # (n = 77: the second word of a half holds 13 patients)
     ps.set(1, row)
     assert np.array_equal(ps[1], row)
     assert not ps[0].any()

@@ -5,9 +5,11 @@
 //
 // Every kernel runs `CHAINS` independent dependency chains per thread of ONE instruction kind written as volatile inline PTX
 // (the compiler can neither drop nor merge them; cuobjdump -sass of this file shows the expected opcode counts), on
-// 148 x 8 CTAs of 256 threads (64 warps per SM = 16 per sub-partition), timed with CUDA events after a warm-up; the SM clock
-// is read through NVML-free means: clock64() deltas against the event time give the effective SM frequency of the run.
-// Output: one JSON object with warp-instructions per clock per SM and per second for each kind.
+// 148 x 8 CTAs of 256 threads, timed with CUDA events after a warm-up (best of 5).  The measured quantity is warp
+// instructions per SECOND; the per-clock figures divide by the device's maximum SM clock (cudaDevAttrClockRate: 1,965 MHz on
+// B200, which bench.py's NVML samples show the join kernels run at), so they are lower bounds if the clock dipped.
+// "max.f32" chains are fused pairwise into FMNMX3 by ptxas: that line counts PTX operations, not SASS instructions.
+// Output: one JSON object with warp-instructions per second and per clock per SM for each kind.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(256) bench_kernel(uint32_t* out, int trips, un
   if (threadIdx.x == 0 && blockIdx.x == 0) clocks[0] = t1 - t0;
 }
 
+static double g_clock_hz = 1.965e9;
+
 template <int K>
 static void run(int sm_count, int ctas_per_sm, uint32_t* d_out, unsigned long long* d_clk, bool first) {
   const int trips = 4096, grid = sm_count * ctas_per_sm;
@@ -103,11 +107,11 @@ static void run(int sm_count, int ctas_per_sm, uint32_t* d_out, unsigned long lo
   const double warp_inst = (double)grid * 8 /*warps per CTA*/ * trips * (double)(UNROLL * CHAINS);
   const double all_inst = warp_inst + (double)grid * 8 * trips * 2.0;
   const double sec = best_ms * 1e-3;
-  const double mhz = clk / sec / 1e6;  // one CTA's clock64() delta over (almost) the whole launch
-  printf("%s\n  {\"kind\": \"%s\", \"ctas_per_sm\": %d, \"ms\": %.4f, \"sm_mhz_effective\": %.0f, \"warp_inst_per_s\": %.4e, "
-         "\"warp_inst_per_clk_per_sm\": %.3f, \"thread_ops_per_clk_per_sm\": %.1f, \"incl_loop_overhead_warp_inst_per_clk_per_sm\": %.3f}",
-         first ? "" : ",", kind_name[K], ctas_per_sm, best_ms, mhz, warp_inst / sec, warp_inst / ((double)clk * sm_count),
-         32.0 * warp_inst / ((double)clk * sm_count), all_inst / ((double)clk * sm_count));
+  (void)clk;
+  const double clks = sec * g_clock_hz * sm_count;  // SM-clocks of the launch at the maximum SM clock
+  printf("%s\n  {\"kind\": \"%s\", \"ctas_per_sm\": %d, \"ms\": %.4f, \"warp_inst_per_s\": %.4e, "
+         "\"warp_inst_per_clk_per_sm\": %.3f, \"thread_ops_per_clk_per_sm\": %.1f, \"incl_loop_overhead_warp_inst_per_s\": %.4e}",
+         first ? "" : ",", kind_name[K], ctas_per_sm, best_ms, warp_inst / sec, warp_inst / clks, 32.0 * warp_inst / clks, all_inst / sec);
 }
 
 int main() {
@@ -116,11 +120,15 @@ int main() {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   sm_count = prop.multiProcessorCount;
+  int khz = 0;
+  CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+  g_clock_hz = khz * 1e3;
   uint32_t* d_out;
   unsigned long long* d_clk;
   CK(cudaMalloc(&d_out, 64));
   CK(cudaMalloc(&d_clk, 64));
-  printf("{\"device\": \"%s\", \"sm_count\": %d, \"chains_per_thread\": %d, \"threads_per_cta\": 256, \"results\": [", prop.name, sm_count, CHAINS);
+  printf("{\"device\": \"%s\", \"sm_count\": %d, \"sm_clock_mhz_max\": %.0f, \"chains_per_thread\": %d, \"threads_per_cta\": 256, \"results\": [", prop.name,
+         sm_count, g_clock_hz / 1e6, CHAINS);
   const int cps = 8;  // 8 CTAs x 8 warps = 64 warps per SM (16 per sub-partition)
   run<POPC>(sm_count, cps, d_out, d_clk, true);
   run<LOP3>(sm_count, cps, d_out, d_clk, false);
