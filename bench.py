@@ -65,6 +65,10 @@ def parse_args():
                     help="permutations scored per pass over the level schedule; more are processed as sequential batches of this size with the "
                          "masks resident on the device (permutations are independent: maxima concatenate, the top-K is the same in every batch). "
                          "Keeps the per-row count tables the joins hand from level to level (2 KB per row, half and 1,024 permutations) inside HBM")
+    ap.add_argument("--cpu-edges", type=int, default=0,
+                    help="CPU leg on a SUB-SHAPE: the same cohort size (identical W) and value table, but a network of this many edges (default: "
+                         "the benchmarked network up to 20,000 patients, n_edges / 20 above - the reference replays levels 1-3 on the host first "
+                         "and keeps an (n+1)^2 table per method-2 thread, SURVEY App. D)")
     ap.add_argument("--cpu-perms", type=int, default=1000, help="permutations the CPU baseline / parity leg scores (the reference's cost per pair*perm does not depend on the count)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: max(10, --steps))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per method for the baseline sample")
@@ -195,9 +199,16 @@ def workload_file(w, a):
 
     cpu_perms = cpu_perm_count(w, a)
 
-    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
-    path = os.path.join(d, f"gcre_bench_workload_{os.getpid()}.npz")
     net = w.net
+    need = w.value_table.nbytes + w.gene_bits.nbytes + w.gene_bits2.nbytes + (64 << 20)
+    d = tempfile.gettempdir()
+    try:
+        st = os.statvfs("/dev/shm")
+        if os.access("/dev/shm", os.W_OK) and st.f_bavail * st.f_frsize > need:
+            d = "/dev/shm"
+    except OSError:
+        pass
+    path = os.path.join(d, f"gcre_bench_workload_{os.getpid()}.npz")
     np.savez(path, n_cases=w.n_cases, n_ctrls=w.n_ctrls, n_perms=cpu_perms, gene_bits=w.gene_bits, gene_bits2=w.gene_bits2,
              perm_masks=w.perm_masks[:cpu_perms], value_table=w.value_table, n_genes=net.n_genes, edges_src=net.edges_src, edges_trg=net.edges_trg,
              edges_sign=net.edges_sign, ents2=net.ents2, path_length=a.path_length)
@@ -1068,11 +1079,27 @@ def main():
         w.value_table = state["method1"]["ex"].getValueTable()
     if rank == 0 and world == 1 and not a.no_cpu_baseline and w.value_table is not None and a.path_length >= 4:
         arm = None
+        cpu_edges = a.cpu_edges or (a.n_edges if w.n_patients <= 20000 else max(2000, a.n_edges // 20))
         try:
-            arm = ReferenceArm(w, a)
-            cpu, ref_out = arm.sample(a.cpu_seconds, results=True)
-            parity = check_parity(ref_out, last_out, state, lv["4"], w, api, cpu_perm_count(w, a),
-                                  lambda st: st["ex"].setPermutedMasks(w.perm_masks[:batch_perms]))
+            if cpu_edges >= a.n_edges:
+                arm = ReferenceArm(w, a)
+                cpu, ref_out = arm.sample(a.cpu_seconds, results=True)
+                parity = check_parity(ref_out, last_out, state, lv["4"], w, api, cpu_perm_count(w, a),
+                                      lambda st: st["ex"].setPermutedMasks(w.perm_masks[:batch_perms]))
+            else:
+                # where the reference cannot run the shape, time the largest runnable sub-shape with identical W - the same
+                # cohort size, permutations and value table over a smaller network (its cost per pair*perm depends on W and I only)
+                a_sub = argparse.Namespace(**vars(a))
+                a_sub.n_edges, a_sub.n_genes = cpu_edges, max(200, int(a.n_genes * cpu_edges / a.n_edges))
+                w_sub = synth.make_workload(a.n_cases, a.n_ctrls, a_sub.n_genes, a_sub.n_edges, cpu_perm_count(w, a), a.seed, max_path_length=a.path_length,
+                                            real_table=True, host_table=False)
+                w_sub.value_table = w.value_table
+                arm = ReferenceArm(w_sub, a_sub)
+                cpu = arm.sample(a.cpu_seconds)
+                cpu["sample"] = (f"SUB-SHAPE with the benchmark's W64 and value table: {w_sub.n_patients} patients, {w_sub.net.n_genes} genes, {a_sub.n_edges} edges "
+                                 f"({w_sub.net.levels['4'].n_pairs} level-4 pairs); ") + cpu["sample"]
+                parity = {"checked": False, "why": "the CPU leg ran a sub-shape (smaller network); parity of this cohort size is covered by tests/test_fullsize_gpu.py "
+                                                   "and the 32-bit-carrier tests"}
         except AssertionError:
             raise
         except Exception as e:  # the GPU numbers stand on their own
