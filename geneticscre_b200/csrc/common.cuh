@@ -63,6 +63,7 @@ struct JoinParams {
   const double* diagD;     // vt[c][total-c]                       (true scores)
   const float* diagF;      // (float) vt[c][total-c]               (method-1 permutation look-ups)
   const double* diagDM;    // max(vt[c][total-c], vt[total-c][c])  (method-2 permutation look-ups)
+  const float* diagFM;     // diagDM rounded UP to f32: upper bounds for the "can any permutation beat the maxima" test
   // outputs
   int* perm_max;           // float bit patterns, >= +0.0f, merged with integer atomicMax
   Cand* cand;

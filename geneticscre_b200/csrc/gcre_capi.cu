@@ -339,6 +339,7 @@ struct gcre_exec {
   double* d_diagD = nullptr;
   float* d_diagF = nullptr;
   double* d_diagDM = nullptr;
+  float* d_diagFM = nullptr;
   long long diag_cap = -1;
   float2* d_env = nullptr;       // envelopes of the permutation look-up table rows (join_screen.cuh), built on first use
   long long env_cap = -1;
@@ -549,7 +550,7 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
     ex->uidsets.clear();
   }
   for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
-                  (void*)ex->d_diagDM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk, (void*)ex->d_env, (void*)ex->d_thr})
+                  (void*)ex->d_diagDM, (void*)ex->d_diagFM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk, (void*)ex->d_env, (void*)ex->d_thr})
     dev_free(ex, p);
   ex->retry.release();
   ex->seed.release();
@@ -1217,27 +1218,31 @@ static int ensure_diag(gcre_exec* ex, long long t_needed) {
   dev_free(ex, ex->d_diagD);
   dev_free(ex, ex->d_diagF);
   dev_free(ex, ex->d_diagDM);
+  dev_free(ex, ex->d_diagFM);
   ex->d_diagD = nullptr;
   ex->d_diagF = nullptr;
   ex->d_diagDM = nullptr;
+  ex->d_diagFM = nullptr;
   ex->diag_cap = -1;
   dev_free(ex, ex->d_env);
   ex->d_env = nullptr;
   ex->env_cap = -1;
   const size_t entries = (size_t)(cap + 1) * (size_t)(cap + 2) / 2;
   {
-    // (cap+1)(cap+2)/2 entries of 12 (method 1) or 16 (method 2) bytes: 26-34 GB at 65,535 carriers per half-row
+    // (cap+1)(cap+2)/2 entries of 12 (method 1) or 20 (method 2) bytes: 26-43 GB at 65,535 carriers per half-row
     cudaError_t e = dev_alloc(ex, (void**)&ex->d_diagD, entries * 8);
     if (e == cudaSuccess) e = (ex->M == 1) ? dev_alloc(ex, (void**)&ex->d_diagF, entries * 4) : dev_alloc(ex, (void**)&ex->d_diagDM, entries * 8);
+    if (e == cudaSuccess && ex->M != 1) e = dev_alloc(ex, (void**)&ex->d_diagFM, entries * 4);
     if (e != cudaSuccess) {
       cudaGetLastError();
       dev_free(ex, ex->d_diagD);
       ex->d_diagD = nullptr;
       return fail(GCRE_ERR_NOMEM, "anti-diagonal value tables for joined rows of up to %lld carriers need %zu bytes of device memory (%s); "
-                  "the limit is set by the densest operand rows", t_needed, entries * (ex->M == 1 ? 12 : 16), cudaGetErrorString(e));
+                  "the limit is set by the densest operand rows", t_needed, entries * (ex->M == 1 ? 12 : 20), cudaGetErrorString(e));
     }
   }
-  build_diag_kernel<<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_vt, ex->vt_rows, ex->vt_cols, (unsigned)cap, ex->d_diagD, ex->d_diagF, ex->d_diagDM);
+  build_diag_kernel<<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_vt, ex->vt_rows, ex->vt_cols, (unsigned)cap, ex->d_diagD, ex->d_diagF, ex->d_diagDM,
+                                                                 ex->d_diagFM);
   CK(cudaGetLastError());
       LAUNCHED();
   ex->diag_cap = cap;
@@ -1784,6 +1789,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   jp.diagD = ex->d_diagD;
   jp.diagF = ex->d_diagF;
   jp.diagDM = ex->d_diagDM;
+  jp.diagFM = ex->d_diagFM;
   jp.perm_max = ex->d_perm_max;
   jp.cand_count = ex->d_scalars;
   jp.max_total = ex->d_scalars + 1;

@@ -44,14 +44,12 @@ constexpr int WARPS = THREADS / 32;
 constexpr int PB = 64;          // partners per unit
 constexpr int FLUSH_AT = 240;   // carrier slots accumulated in the 8 bit planes before they are flushed into u16 counters
 constexpr int QCAP = 96;        // per-warp queue of filtered partner carriers (drained at 64)
-// Resident CTAs per SM asked of ptxas (= register budget).  Measured on B200 with the level-4 join of BASELINE config 3
-// (12 M pairs, ms per launch): method 1: 4 CTAs (128 regs) 19.9, 5: 17.4, 6: 16.2, 8 (64 regs, 164 B spilled) 15.0;
-// method 2: 4: 33.9, 5: 39.1, 6: 40.2, 8: 40.0.  Keeping the per-permutation state in shared memory instead (no
-// spills at 48 regs, 1,000 SASS instructions) was slower for both (22 / 35 ms): the kernel is issue-bound.
-// Method 2 again after its two halves were rolled into one loop (counts parked in shared memory): 4 CTAs (128 regs) 20.2 ms,
-// 5 (96 regs, no spills) 19.0, 6 (80 regs, 84 B spilled) 26.4.
+// Resident CTAs per SM asked of ptxas (= register budget).  Round 1 (32 running maxima per lane in registers) measured on the
+// level-4 join of BASELINE config 3: method 1 best at 8 CTAs (64 registers, 164 B spilled), method 2 at 5 (96 registers).
+// With the thresholded look-ups (no running maxima) both compile to 64 registers without spills: 8 CTAs = 32 warps per SM;
+// method 1 also fits 48 registers (10 CTAs).  Measured choices: profiles/r2_occupancy_variants.txt.
 #ifndef GCRE_SPARSE_MB2
-#define GCRE_SPARSE_MB2 5
+#define GCRE_SPARSE_MB2 8
 #endif
 #ifndef GCRE_SPARSE_MB1
 #define GCRE_SPARSE_MB1 8
@@ -297,7 +295,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
   // method 2: the two halves go through ONE instance of the filter / accumulate / flush code (a rolled loop), their counts
   // parked here for the look-up stage: unrolled per half the kernel was 62 KB of SASS and lost more issue slots to
   // instruction fetch than to memory latency (profiles/r1_sparse_final_full.txt, no_instruction 4.1 vs long_scoreboard 4.0)
-  __shared__ uint32_t s_cnt[M == 2 ? 2 : 1][M == 2 ? 16 : 1][THREADS];
+  // method 2 parks the counts of half 0 here while half 1 accumulates (the last half stays in registers for the look-ups)
+  __shared__ uint32_t s_cnt[1][M == 2 ? 16 : 1][THREADS];
 
   const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Wp = a.Wp, Iw = a.Iw;  // Iw: words per patient row of pt (a multiple of 32: every lane owns a valid word)
@@ -306,18 +305,27 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
   const unsigned lt_mask = (1u << lane) - 1u;
   uint32_t* queue = s_queue[warp];
 
-  float best[32];
-#pragma unroll
-  for (int b = 0; b < 32; b++) best[b] = 0.0f;
+  // Thresholded look-ups.  The per-permutation maxima live in global memory only (a.perm_max, float bit patterns >= +0, raised
+  // with atomicMax).  A lane keeps ONE float, thr: a lower bound of the current maxima of its 32 permutations (their minimum when
+  // last read - maxima only grow).  A pair's look-ups first only ask "does any permutation score above thr?" (one compare per
+  // look-up, no running-maximum registers); only then - a few times per thousand pairs once the maxima have settled - the pair's
+  // exact scores are pushed with atomicMax and thr is re-read.  Method 2 asks the question with round-up f32 copies of its f64
+  // table and a round-up add, an upper bound of the exactly rounded f64 sum, and computes the f64 sums only in the rare path.
+  // Compared with 32 running maxima per lane this frees 31 registers (method 2: 96 -> 72, 5 -> 7 CTAs per SM).
+  float thr = 0.0f;
   int pb_cur = -1;
-
-  auto flush_best = [&](int pb) {
+  unsigned since_refresh = 0;
+  auto load_thr = [&](int pb) -> float {
     const int r0 = (pb * 32 + lane) * 32;
-    if (r0 < a.Ip) {
+    if (r0 >= a.Ip) return INFINITY;  // no result slots: the lane's permutations are padding copies of real ones
+    const int4* p = reinterpret_cast<const int4*>(a.perm_max + r0);
+    float m = INFINITY;
 #pragma unroll
-      for (int b = 0; b < 32; b++)
-        if (best[b] > 0.0f) atomicMax(a.perm_max + r0 + b, __float_as_int(best[b]));
+    for (int q = 0; q < 8; q++) {
+      const int4 v = __ldcg(p + q);
+      m = fminf(fminf(m, __int_as_float(v.x)), fminf(__int_as_float(v.y), fminf(__int_as_float(v.z), __int_as_float(v.w))));
     }
+    return m;
   };
 
   while (true) {
@@ -337,10 +345,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       pb = (int)(g / s.n_units);
       unit = s.unit_begin + (g % s.n_units);
     }
-    if (pb != pb_cur) {
-      if (pb_cur >= 0) flush_best(pb_cur);
-#pragma unroll
-      for (int b = 0; b < 32; b++) best[b] = 0.0f;
+    if (pb != pb_cur || (++since_refresh & 7u) == 0u) {  // other warps keep raising the maxima: re-read every 8th unit
+      thr = load_thr(pb);
       pb_cur = pb;
     }
     const bool first_pb = !RETRY && (pb == 0);
@@ -504,9 +510,13 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           ncnh = s.ncase1[item] - ncnh;
         }
         if (M == 2) {
+          if (h == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; i++) s_cnt[h][i][tid] = c16[i];
-          if (h == 0) { nd[0] = ndh; ncn[0] = ncnh; pitem[0] = item; } else { nd[M - 1] = ndh; ncn[M - 1] = ncnh; pitem[M - 1] = item; }
+            for (int i = 0; i < 16; i++) s_cnt[0][M == 2 ? i : 0][tid] = c16[i];
+            nd[0] = ndh; ncn[0] = ncnh; pitem[0] = item;
+          } else {
+            nd[M - 1] = ndh; ncn[M - 1] = ncnh; pitem[M - 1] = item;
+          }
         } else {
           nd[0] = ndh;
           ncn[0] = ncnh;
@@ -519,68 +529,70 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       if (!empty || !base_done) {
         if (empty) base_done = true;
         if (PC) {
-          // counts = base + P[partner] - overlap, packed u16 pairs (whole-register arithmetic is exact: every final half
-          // is a count in [0, 65535]); register i holds permutation bits b = ((i & 1) * 2 + hf) * 8 + (i >> 1), hf = 0, 1
+          // counts = base + P[partner] - overlap, packed u16 pairs (whole-register arithmetic is exact: every final half is a
+          // count in [0, 65535]); finalised in place: half 0 of method 2 in its shared-memory slots, the last half in c16
           const uint4* P0 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[0] * s.n_perm_blocks + pb) * 4) * 32 + lane;
-          if (M == 1) {
-            const unsigned total = t0[0] + nd[0];
-            const float* row = a.diagF + diag_base(total);
+          const uint4* P1 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[M - 1] * s.n_perm_blocks + pb) * 4) * 32 + lane;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint4 pv = __ldg(P0 + q * 32);
-              const uint32_t pr[4] = {pv.x, pv.y, pv.z, pv.w};
+          for (int q = 0; q < 4; q++) {
+            const uint4 pv = __ldg(P1 + q * 32);
+            const uint32_t pr[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const int i = 4 * q + k;
-                const uint32_t v = s_base[0][i][tid] + pr[k] - c16[i];
-                best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __ldg(row + (v & 0xffffu)));
-                best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __ldg(row + (v >> 16)));
-              }
-            }
-          } else {
-            const uint4* P1 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[M - 1] * s.n_perm_blocks + pb) * 4) * 32 + lane;
-            const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
-            const double* rowp = a.diagDM + diag_base(tp);
-            const double* rown = a.diagDM + diag_base(tn) + tn;
+            for (int k = 0; k < 4; k++) c16[4 * q + k] = s_base[M - 1][4 * q + k][tid] + pr[k] - c16[4 * q + k];
+            if (M == 2) {
+              const uint4 pw = __ldg(P0 + q * 32);
+              const uint32_t pr0[4] = {pw.x, pw.y, pw.z, pw.w};
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint4 pvp = __ldg(P0 + q * 32), pvn = __ldg(P1 + q * 32);
-              const uint32_t prp[4] = {pvp.x, pvp.y, pvp.z, pvp.w}, prn[4] = {pvn.x, pvn.y, pvn.z, pvn.w};
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const int i = 4 * q + k;
-                const uint32_t vp = s_base[0][i][tid] + prp[k] - s_cnt[0][M == 2 ? i : 0][tid];
-                const uint32_t vn = s_base[M - 1][i][tid] + prn[k] - s_cnt[M == 2 ? 1 : 0][M == 2 ? i : 0][tid];
-                // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
-                const double vlo = __ldg(rowp + (vp & 0xffffu)) + __ldg(rown - (vn & 0xffffu));
-                const double vhi = __ldg(rowp + (vp >> 16)) + __ldg(rown - (vn >> 16));
-                best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __double2float_rn(vlo));
-                best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __double2float_rn(vhi));
-              }
+              for (int k = 0; k < 4; k++)
+                s_cnt[0][M == 2 ? 4 * q + k : 0][tid] = s_base[0][4 * q + k][tid] + pr0[k] - s_cnt[0][M == 2 ? 4 * q + k : 0][tid];
             }
           }
-        } else if (M == 1) {
-          const unsigned total = t0[0] + nd[0];
-          const float* row = a.diagF + diag_base(total);
+        }
+        // final counts of permutation bit b: register GCRE_C16_REG(b), half GCRE_C16_HI(b); the last half (method 1: the only
+        // one) is in c16, half 0 of method 2 in shared memory
+        bool hit = false;
+        if (M == 1) {
+          const float* row = a.diagF + diag_base(t0[0] + nd[0]);
 #pragma unroll
           for (int b = 0; b < 32; b++) {
             const uint32_t v = c16[GCRE_C16_REG(b)];
             const uint32_t c = GCRE_C16_HI(b) ? (v >> 16) : (v & 0xffffu);
-            best[b] = fmaxf(best[b], __ldg(row + c));
+            hit |= __ldg(row + c) > thr;
           }
         } else {
-          const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
-          const double* rowp = a.diagDM + diag_base(tp);
-          const double* rown = a.diagDM + diag_base(tn) + tn;
+          // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
+          const unsigned tn = t0[M - 1] + nd[M - 1];
+          const float* frp = a.diagFM + diag_base(t0[0] + nd[0]);
+          const float* frn = a.diagFM + diag_base(tn) + tn;
 #pragma unroll
           for (int b = 0; b < 32; b++) {
-            const uint32_t vp = s_cnt[0][M == 2 ? GCRE_C16_REG(b) : 0][tid], vn = s_cnt[M == 2 ? 1 : 0][M == 2 ? GCRE_C16_REG(b) : 0][tid];
+            const uint32_t vp = s_cnt[0][M == 2 ? GCRE_C16_REG(b) : 0][tid], vn = c16[GCRE_C16_REG(b)];
             const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
             const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
-            // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
-            const double v = __ldg(rowp + cp) + __ldg(rown - cn);
-            best[b] = fmaxf(best[b], __double2float_rn(v));
+            hit |= __fadd_ru(__ldg(frp + cp), __ldg(frn - cn)) > thr;  // >= the exactly rounded f64 sum
           }
+        }
+        if (__any_sync(0xffffffffu, hit)) {
+          // rare: exact scores of the pair -> global maxima.  A rolled loop (small code, no register pressure on the common path):
+          // the last half's counts are copied to a dynamically indexed local array (thread-private memory, touched only here)
+          uint32_t lc[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) lc[i] = c16[i];
+          const int r0 = (pb * 32 + lane) * 32;
+          const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
+#pragma unroll 1
+          for (int b = 0; b < 32; b++) {
+            const int reg = GCRE_C16_REG(b), sh = GCRE_C16_HI(b) * 16;
+            float p;
+            if (M == 1) {
+              p = __ldg(a.diagF + diag_base(tp) + ((lc[reg] >> sh) & 0xffffu));
+            } else {
+              const uint32_t cp = (s_cnt[0][M == 2 ? reg : 0][tid] >> sh) & 0xffffu, cn = (lc[reg] >> sh) & 0xffffu;
+              p = __double2float_rn(__ldg(a.diagDM + diag_base(tp) + cp) + __ldg(a.diagDM + diag_base(tn) + tn - cn));
+            }
+            if (p > thr) atomicMax(a.perm_max + r0 + b, __float_as_int(p));
+          }
+          thr = load_thr(pb);
         }
       }
 
@@ -590,18 +602,13 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 #pragma unroll
         for (int h = 0; h < M; h++) {
           uint4* out = reinterpret_cast<uint4*>(s.pcnt_res) + (((r * M + h) * s.n_perm_blocks + pb) * 4) * 32 + lane;
+          uint32_t v16[16];  // the last half is in registers, half 0 of method 2 in shared memory
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            if (M == 1) __stcs(out + q * 32, make_uint4(c16[4 * q], c16[4 * q + 1], c16[4 * q + 2], c16[4 * q + 3]));
-            else __stcs(out + q * 32, make_uint4(s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q : 0][tid], s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 1 : 0][tid],
-                                          s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 2 : 0][tid], s_cnt[M == 2 ? h : 0][M == 2 ? 4 * q + 3 : 0][tid]));
-          }
-          {  // the range of the lane's 32 counts: all the screening kernel of the next level reads of them
-            uint32_t v16[16];
+          for (int i = 0; i < 16; i++) v16[i] = (h == M - 1) ? c16[i] : s_cnt[0][M == 2 ? i : 0][tid];
 #pragma unroll
-            for (int i = 0; i < 16; i++) v16[i] = (M == 1) ? c16[i] : s_cnt[M == 2 ? h : 0][M == 2 ? i : 0][tid];
-            s.prange_res[((r * M + h) * s.n_perm_blocks + pb) * 32 + lane] = range16(v16);
-          }
+          for (int q = 0; q < 4; q++) __stcs(out + q * 32, make_uint4(v16[4 * q], v16[4 * q + 1], v16[4 * q + 2], v16[4 * q + 3]));
+          // the range of the lane's 32 counts: all the screening kernel of the next level reads of them
+          s.prange_res[((r * M + h) * s.n_perm_blocks + pb) * 32 + lane] = range16(v16);
           if (first_pb && lane == 0) {
             s.len_res[r * M + h] = t0[h == 0 ? 0 : M - 1] + nd[h == 0 ? 0 : M - 1];
             s.ncase_res[r * M + h] = nc0[h == 0 ? 0 : M - 1] + ncn[h == 0 ? 0 : M - 1];
@@ -674,7 +681,6 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     }
     __syncwarp();
   }
-  if (pb_cur >= 0) flush_best(pb_cur);
 }
 
 // u32 carrier indices when n (which is also the sentinel index) does not fit u16; GCRE_TEST_WIDE_CARRIERS=1 (test hook)

@@ -153,8 +153,9 @@ __global__ void masks_to_patient_major_kernel(const uint64_t* __restrict__ masks
 //   D [t(t+1)/2 + c] = vt[c][t-c]
 //   F [..]           = (float) vt[c][t-c]              (method 1 permutation look-ups; NaN -> -1 so it can never win)
 //   DM[..]           = std::max(vt[c][t-c], vt[t-c][c]) (src/methods.h:110-118; std::max(a,b) = a<b ? b : a)
+//   FM[..]           = DM rounded up to f32 (method 2: upper bound used before the exact f64 look-ups, join_sparse.cuh)
 __global__ void build_diag_kernel(const double* __restrict__ vt, int rows, int cols, unsigned t_cap, double* __restrict__ D,
-                                  float* __restrict__ F, double* __restrict__ DM) {
+                                  float* __restrict__ F, double* __restrict__ DM, float* __restrict__ FM) {
   const unsigned t = blockIdx.x;
   if (t > t_cap) return;
   const size_t base = diag_base(t);
@@ -165,7 +166,9 @@ __global__ void build_diag_kernel(const double* __restrict__ vt, int rows, int c
     if (F) F[base + c] = (a != a) ? -1.0f : (float)a;
     if (DM) {
       const double b = (q < (unsigned)rows && c < (unsigned)cols) ? vt[(size_t)q * cols + c] : -1.0;
-      DM[base + c] = (a < b) ? b : a;
+      const double mx = (a < b) ? b : a;
+      DM[base + c] = mx;
+      FM[base + c] = __double2float_ru(mx);  // (NaN stays NaN: it never passes a `>` test, like the exact sum it stands for)
     }
   }
 }

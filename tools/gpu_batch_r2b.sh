@@ -4,6 +4,10 @@ set -u
 OUT=gpurun_out
 python -m pytest tests -m gpu -q > $OUT/r2_gputest2.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_gputest2.log
 python bench.py --steps 20 --warmup 5 > $OUT/r2_bench_b.json 2> $OUT/r2_bench_b.err; echo "bench rc=$?" >> $OUT/r2_bench_b.err
+# occupancy variants of the sparse kernels (resident CTAs per SM for methods 1 / 2), same bench, resident inputs only
+for V in 8_mb2_6 8_mb2_7 10_mb2_8 12_mb2_8 10_mb2_7; do
+  GCRE_B200_LIB=$PWD/build_variants/lib_mb1_$V.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/r2_bench_var_$V.json 2> $OUT/r2_bench_var_$V.err
+done
 bash tools/gpu_batch_profile.sh > $OUT/r2_profile_batch.log 2>&1
 # per-kernel split of the opt-in screening path (launch list only)
 GCRE_SCREEN=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/r2_step_launches_screen.csv \
