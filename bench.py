@@ -327,10 +327,11 @@ class ReferenceArm:
         self.cores = (os.cpu_count() or 1) if self.kind == "reference" else 1
         # method 2 of the reference needs (and leaks) one (n+1)^2 f64 table per worker thread and join: bound both by the RAM
         table_bytes = (w.n_patients + 1) ** 2 * 8
-        budget = 0.4 * mem_available_bytes() - 2 * table_bytes
-        self.threads = {"method1": self.cores, "method2": int(max(1, min(self.cores, budget // table_bytes)))}
+        # (a worker's set-up replays levels 1a, 2 and 3 through the reference: three more joins that leave their copies behind)
+        budget = 0.5 * mem_available_bytes() - 2.5 * table_bytes
+        self.threads = {"method1": self.cores, "method2": int(max(1, min(self.cores, budget // (4 * table_bytes))))}
         self.joins_per_worker = {"method1": REF_JOINS_PER_WORKER["method1"],
-                                 "method2": int(max(1, min(REF_JOINS_PER_WORKER["method2"], budget // (self.threads["method2"] * table_bytes))))}
+                                 "method2": int(max(1, min(REF_JOINS_PER_WORKER["method2"], budget // (self.threads["method2"] * table_bytes) - 3)))}
         self.lv = w.net.levels["4"]
         self.csum = np.cumsum(self.lv.count.astype(np.int64))
         self.path = workload_file(w, a)
@@ -359,10 +360,9 @@ class ReferenceArm:
         """two-point calibration: a join call has a fixed cost (per-thread state; for method 2 a per-thread clone of the
         (n+1)^2 table, src/methods.h:128) plus a per-pair cost"""
         lv = self.lv
-        wk = self._worker(method, need=2)
         x1 = max(64, lv.n_uids // 400)
-        r1 = wk.join(x1)
-        r2 = wk.join(min(lv.n_uids, 4 * x1))
+        r1 = self._worker(method).join(x1)
+        r2 = self._worker(method).join(min(lv.n_uids, 4 * x1))
         rate = max(r2["pairs"] - r1["pairs"], 1) / max(r2["seconds"] - r1["seconds"], 1e-6)
         t_fixed = max(r1["seconds"] - r1["pairs"] / rate, 0.0)
         if t_fixed + lv.n_pairs / rate <= 3.0 * target_s:
@@ -1094,7 +1094,9 @@ def main():
                 w_sub = synth.make_workload(a.n_cases, a.n_ctrls, a_sub.n_genes, a_sub.n_edges, cpu_perm_count(w, a), a.seed, max_path_length=a.path_length,
                                             real_table=True, host_table=False)
                 w_sub.value_table = w.value_table
-                arm = ReferenceArm(w_sub, a_sub)
+                # method 1 only: at this cohort size every method-2 thread needs its own (n+1)^2 f64 table (20 GB at 50,000 patients),
+                # copied again for every join and never freed - one thread would be all this host can hold
+                arm = ReferenceArm(w_sub, a_sub, methods=("method1",))
                 cpu = arm.sample(a.cpu_seconds)
                 cpu["sample"] = (f"SUB-SHAPE with the benchmark's W64 and value table: {w_sub.n_patients} patients, {w_sub.net.n_genes} genes, {a_sub.n_edges} edges "
                                  f"({w_sub.net.levels['4'].n_pairs} level-4 pairs); ") + cpu["sample"]

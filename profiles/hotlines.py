@@ -56,12 +56,13 @@ def main():
             data.append(r)
     fns = sass_lines(ksub)
     # pick the disassembled function whose demangled-ish name matches template args of the profiled kernel
-    m = re.search(r"<\(int\)(\d), \(bool\)(\d)(?:, (unsigned short|unsigned int))?(?:, \(bool\)(\d))?>", kname)
-    key = f"ILi{m.group(1)}ELb{m.group(2)}E" if m else ""
-    if m and m.group(3):
-        key += {"unsigned short": "t", "unsigned int": "j"}[m.group(3)]
-    if m and m.group(4):
-        key += f"Lb{m.group(4)}E"
+    # mangled template-argument string of the profiled instance: (int)N -> LiNE, (bool)B -> LbBE, unsigned short -> t, unsigned int -> j
+    targs = re.search(r"<(.*?)>\(", kname)
+    key = "I"
+    for a in (targs.group(1).split(", ") if targs else []):
+        mi, mb = re.match(r"\(int\)(\d+)", a), re.match(r"\(bool\)(\d)", a)
+        key += f"Li{mi.group(1)}E" if mi else f"Lb{mb.group(1)}E" if mb else {"unsigned short": "t", "unsigned int": "j"}.get(a, "")
+    key += "E"
     fn = [f for f in fns if ksub in f and key in f][0]
     ins = fns[fn]
     assert len(ins) == len(data), (len(ins), len(data))
