@@ -687,8 +687,7 @@ def main():
             else:
                 for k in info:
                     info_sum[k]["kernel_ms"] += info[k]["kernel_ms"]
-                    info_sum[k]["exact_units"] += info[k].get("exact_units", 0)
-                    info_sum[k]["total_units"] += info[k].get("total_units", 0)
+                    info_sum[k]["exact_pairs"] += info[k].get("exact_pairs", 0)
             res_last = res
         st["batch"] = 0
         return info_sum, res_last, res_first
@@ -888,8 +887,8 @@ def main():
             for k in names:
                 inf = last_out[method][0][k]
                 kms = float(inf["kernel_ms"])
-                per_level[method][k] = {"pairs": int(inf["pairs"]), "kernel_ms": kms, "kernel": {1: "dense", 2: "sparse"}.get(inf["kernel"], "none") + ("+precount" if inf.get("precounted") else "") + ("+split-carrier" if inf.get("split_carrier") else "") + ("+screened" if inf.get("screened") else ""),
-                                        "exact_fraction": (inf["exact_units"] / inf["total_units"]) if inf.get("screened") and inf.get("total_units") else None,
+                per_level[method][k] = {"pairs": int(inf["pairs"]), "kernel_ms": kms, "kernel": {1: "dense", 2: "sparse"}.get(inf["kernel"], "none") + ("+precount" if inf.get("precounted") else "") + ("+split-carrier" if inf.get("split_carrier") else "") + ("+thresholded" if inf.get("thresholded") else ""),
+                                        "exact_lookup_fraction": (inf["exact_pairs"] / max(1, inf["pairs"] * ((batch_perms + 1023) // 1024) * n_batches)) if inf.get("thresholded") else None,
                                         "pair_perm_per_s": (inf["pairs"] * w.n_perms / (kms * 1e-3)) if kms > 0 else None}
 
     # ---- end-to-end through the reference-facing calls with HOST buffers (R-facing int matrices), N GPUs ----

@@ -25,7 +25,6 @@
 #include "join_dense.cuh"
 #include "join_sparse.cuh"
 #include "join_sparse_sc.cuh"
-#include "join_screen.cuh"
 #include "value_table.cuh"
 #include "decorated.cuh"
 
@@ -341,15 +340,12 @@ struct gcre_exec {
   double* d_diagDM = nullptr;
   float* d_diagFM = nullptr;
   long long diag_cap = -1;
-  float2* d_env = nullptr;       // envelopes of the permutation look-up table rows (join_screen.cuh), built on first use
-  long long env_cap = -1;
-  float* d_thr = nullptr;        // per-lane screening thresholds [Iw]
   // outputs / scratch
   int* d_perm_max = nullptr;
   unsigned long long* d_topk = nullptr;  // [0] self-tightening candidate threshold, [1..64] its hash-bucket maxima (JoinParams::slots)
   unsigned* d_scalars = nullptr;  // [0] candidate count, [1] max_total, [2..3] 64-bit work counter of the sparse kernel,
-                                  // [4] seed entries, [5] retry entries of a screened join, [6..7] work counter of its exact passes
-  DevBuf cand, scratch, scan_tmp, retry, seed;
+                                  // [4..5] 64-bit count of pairs that took the exact path of the thresholded look-ups (diagnostic)
+  DevBuf cand, scratch, scan_tmp;
   unsigned* h_scalars = nullptr;  // pinned
   // page-locked landing area of a join's results: [kSpecCand candidates][Ip permutation maxima].  They are copied behind every
   // launch together with the scalars, so a join waits for the device once instead of three times.
@@ -396,7 +392,6 @@ static void drop_view(gcre_pathset* ps) {
   dev_free(ps->ex, ps->view.ncase);
   dev_free(ps->ex, ps->view.car);
   dev_free(ps->ex, ps->view.pcnt);
-  dev_free(ps->ex, ps->view.prange);
   ps->view = SparseView();
 }
 
@@ -506,7 +501,7 @@ extern "C" int gcre_exec_create(int method, int num_cases, int num_ctrls, int it
     CK(pool_stream(device, &ex->copy_stream));
     CK(pool_event(device, false, &ex->ev_copy));
     CK(pool_event(device, false, &ex->ev_order));
-    for (DevBuf* b : {&ex->cand, &ex->scratch, &ex->scan_tmp, &ex->retry, &ex->seed}) b->owner = ex;
+    for (DevBuf* b : {&ex->cand, &ex->scratch, &ex->scan_tmp}) b->owner = ex;
     CK(dev_alloc(ex, (void**)&ex->d_masks, std::max<size_t>((size_t)iters * ex->W64, 1) * 8));
     CK(dev_alloc(ex, (void**)&ex->d_pm, (size_t)ex->Wp * ex->Ip * 8));
     CK(cudaMemsetAsync(ex->d_masks, 0, std::max<size_t>((size_t)iters * ex->W64, 1) * 8, ex->stream));
@@ -550,10 +545,8 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
     ex->uidsets.clear();
   }
   for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
-                  (void*)ex->d_diagDM, (void*)ex->d_diagFM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk, (void*)ex->d_env, (void*)ex->d_thr})
+                  (void*)ex->d_diagDM, (void*)ex->d_diagFM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk})
     dev_free(ex, p);
-  ex->retry.release();
-  ex->seed.release();
   ex->cand.release();
   ex->scan_tmp.release();
   ex->scratch.release();
@@ -1224,9 +1217,6 @@ static int ensure_diag(gcre_exec* ex, long long t_needed) {
   ex->d_diagDM = nullptr;
   ex->d_diagFM = nullptr;
   ex->diag_cap = -1;
-  dev_free(ex, ex->d_env);
-  ex->d_env = nullptr;
-  ex->env_cap = -1;
   const size_t entries = (size_t)(cap + 1) * (size_t)(cap + 2) / 2;
   {
     // (cap+1)(cap+2)/2 entries of 12 (method 1) or 20 (method 2) bytes: 26-43 GB at 65,535 carriers per half-row
@@ -1246,24 +1236,6 @@ static int ensure_diag(gcre_exec* ex, long long t_needed) {
   CK(cudaGetLastError());
       LAUNCHED();
   ex->diag_cap = cap;
-  return GCRE_OK;
-}
-
-// envelopes of the permutation look-up rows for the screening kernel (join_screen.cuh); follows ensure_diag
-static int ensure_env(gcre_exec* ex) {
-  if (ex->d_env && ex->env_cap == ex->diag_cap) return GCRE_OK;
-  dev_free(ex, ex->d_env);
-  ex->d_env = nullptr;
-  ex->env_cap = -1;
-  const long long cap = ex->diag_cap;
-  if (cap < 0) return fail(GCRE_ERR_ARG, "no value table layout to build envelopes from");
-  const size_t entries = (size_t)(cap + 1) * (size_t)(cap + 2) / 2;
-  CK(dev_alloc(ex, (void**)&ex->d_env, entries * sizeof(float2)));
-  if (ex->M == 1) build_env_kernel<float><<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_diagF, (unsigned)cap, ex->n_cases, ex->n, ex->d_env);
-  else build_env_kernel<double><<<(unsigned)(cap + 1), 128, 0, ex->stream>>>(ex->d_diagDM, (unsigned)cap, ex->n_cases, ex->n, ex->d_env);
-  CK(cudaGetLastError());
-  LAUNCHED();
-  ex->env_cap = cap;
   return GCRE_OK;
 }
 
@@ -1323,14 +1295,13 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
   CKS(materialize_zero(ps));
   {  // (re)build lists and stats; counts emitted with the rows stay - the rows have not changed
     uint32_t* pcnt = ps->view.pcnt;
-    uint32_t* prange = ps->view.prange;
-    const unsigned long long gen = ps->view.pcnt_gen;
+    const unsigned long long gen = ps->view.pcnt_gen, elo = ps->view.emit_lo, ehi = ps->view.emit_hi;
     ps->view.pcnt = nullptr;
-    ps->view.prange = nullptr;
     drop_view(ps);
     ps->view.pcnt = pcnt;
-    ps->view.prange = prange;
     ps->view.pcnt_gen = gen;
+    ps->view.emit_lo = elo;
+    ps->view.emit_hi = ehi;
   }
   const long long items = (long long)ps->size * ex->M;
   CK(dev_alloc(ex, (void**)&ps->view.off, (size_t)(items + 1) * 8));
@@ -1384,9 +1355,7 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
 static int ensure_precount(gcre_exec* ex, gcre_pathset* ps) {
   if (ps->view.pcnt && ps->view.pcnt_gen == ex->mask_gen) return GCRE_OK;
   dev_free(ex, ps->view.pcnt);
-  dev_free(ex, ps->view.prange);  // (ranges of emitted counts belong to the table they were emitted with)
   ps->view.pcnt = nullptr;
-  ps->view.prange = nullptr;
   const long long items = (long long)ps->size * ex->M;
   const int nb = ex->Iw / 32;
   CK(dev_alloc(ex, (void**)&ps->view.pcnt, std::max<size_t>((size_t)items * nb, 1) * 2048));
@@ -1683,7 +1652,6 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   if (kernel == GCRE_KERNEL_SPARSE && !sparse_supported(ex->n, t_needed, ex->Iw)) kernel = GCRE_KERNEL_DENSE;
   SparseParams sp;
   memset(&sp, 0, sizeof sp);
-  bool screen_on = false;
   if (kernel == GCRE_KERNEL_SPARSE) {
     CKS(ensure_patient_major(ex));
     // upstream operand: rows that came out of a KEEP join carry their counts and totals - no carrier lists needed
@@ -1699,6 +1667,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     sp.unit_idx = (const uint32_t*)us->unit_idx.p;
     sp.work_counter = (unsigned long long*)(ex->d_scalars + 2);
     sp.n_perm_blocks = ex->Iw / 32;
+    sp.exact_pairs = reinterpret_cast<unsigned long long*>(ex->d_scalars + 4);
     size_t budget = (size_t)24 << 30;  // device bytes a table of per-permutation counts may take (GCRE_PRECOUNT_MAX_MB overrides)
     if (const char* mb = std::getenv("GCRE_PRECOUNT_MAX_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
     // kept rows take their counts along (join_sparse.cuh) when result rows are the running sums of the counts (res_is_prefix:
@@ -1710,16 +1679,6 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
                       (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
     int pc_mode = emit ? PRECOUNT_NO : precount_mode(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget);
     if (few_perms && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;  // the split-carrier kernel is the better form there
-    // Range-bound screening (join_screen.cuh): score-only joins whose upstream rows carry their counts AND count ranges.
-    // Opt-in (GCRE_SCREEN=1): measured on BASELINE config 3 the screening pass costs as much as the exact kernel it replaces
-    // (gathers and the filter dominate a pair, not the look-ups it saves) - profiles/r2_bench_screen_ab.txt.
-    // GCRE_TEST_SCREEN=1 (test hook) runs it on joins of any size.
-    {
-      const char* scr = std::getenv("GCRE_SCREEN");
-      const bool want = (scr && *scr == '1') || std::getenv("GCRE_TEST_SCREEN") != nullptr;
-      screen_on = want && !keep && base_emitted && paths0->view.prange && !few_perms && pc_mode != PRECOUNT_YES;
-      if (screen_on && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;
-    }
     if (pc_mode == PRECOUNT_SAMPLE) {
       // how much of a partner row is already in its upstream row: 2,048 pairs spread over the join (~40 us incl. the read-back)
       JoinParams q;
@@ -1755,11 +1714,9 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
       CK(dev_alloc(ex, (void**)&paths_res->view.pcnt, items * sp.n_perm_blocks * 2048));
       CK(dev_alloc(ex, (void**)&paths_res->view.len, items * 4));
       CK(dev_alloc(ex, (void**)&paths_res->view.ncase, items * 4));
-      CK(dev_alloc(ex, (void**)&paths_res->view.prange, items * sp.n_perm_blocks * 128));
       sp.pcnt_res = paths_res->view.pcnt;
       sp.len_res = paths_res->view.len;
       sp.ncase_res = paths_res->view.ncase;
-      sp.prange_res = paths_res->view.prange;
     }
   }
 
@@ -1839,8 +1796,8 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   unsigned long long thr_key = score_key(-std::numeric_limits<double>::infinity());
   double kernel_ms = 0.0;
   int launches = 0;
-  bool screened = false;
-  unsigned long long screened_units = 0, exact_units = 0;
+  bool thresholded = false;
+  unsigned long long exact_pairs = 0;
   for (size_t si = 0; si < plan.size(); si++) {
     const Seg seg = plan[si];
     const unsigned long long p = seg.b, pe = seg.e;
@@ -1855,54 +1812,12 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
       sp.unit_begin = p;
       sp.n_units = pe - p;
       CK(cudaMemsetAsync(ex->d_scalars + 2, 0, 6 * sizeof(unsigned), ex->stream));
-      const bool screen_seg = screen_on && (sp.n_units >= screen::MIN_UNITS || std::getenv("GCRE_TEST_SCREEN") != nullptr);
-      if (screen_seg) {
-        // seed (exact, every stride-th unit) -> thresholds -> screening pass over all units -> exact pass over what it flagged
-        int stride = screen::SEED_STRIDE;
-        if (const char* e = std::getenv("GCRE_TEST_SCREEN_STRIDE")) stride = std::max(1, std::atoi(e));
-        const unsigned long long n_seed = (sp.n_units + stride - 1) / stride * (unsigned long long)sp.n_perm_blocks;
-        const unsigned long long n_all = sp.n_units * (unsigned long long)sp.n_perm_blocks;
-        if (n_all > 0xfffffff0ull) return fail(GCRE_ERR_ARG, "join too large: more than 2^32 work items");
-        CKS(ensure_env(ex));
-        if (!ex->d_thr) CK(dev_alloc(ex, (void**)&ex->d_thr, (size_t)ex->Iw * 4));
-        CKS(ex->seed.ensure((size_t)n_seed * sizeof(RetryEntry)));
-        CKS(ex->retry.ensure((size_t)n_all * sizeof(RetryEntry)));
-        screen_seed_list_kernel<<<grid_for((long long)n_seed, 256), 256, 0, ex->stream>>>(sp.unit_begin, sp.n_units, stride, sp.n_perm_blocks,
-                                                                                          (RetryEntry*)ex->seed.p, ex->d_scalars + 4);
-        CK(cudaGetLastError());
-        LAUNCHED();
-        SparseParams sr = sp;
-        sr.retry = (const RetryEntry*)ex->seed.p;
-        sr.retry_count = ex->d_scalars + 4;
-        sr.work_counter = (unsigned long long*)(ex->d_scalars + 6);
-        CK(launch_join_sparse_retry(ex->stream, jp, sr, ex->M, ex->sm_count));
-        LAUNCHED();
-        screen_thresholds_kernel<<<grid_for(ex->Iw, 128), 128, 0, ex->stream>>>(ex->d_perm_max, ex->iters, ex->Iw, ex->d_thr);
-        CK(cudaGetLastError());
-        LAUNCHED();
-        ScreenParams zp;
-        zp.prange0 = paths0->view.prange;
-        zp.env = ex->d_env;
-        zp.thr = ex->d_thr;
-        zp.retry = (RetryEntry*)ex->retry.p;
-        zp.retry_count = ex->d_scalars + 5;
-        if (ex->M == 1) CK(launch_join_screen<1>(ex->stream, jp, sp, zp, ex->sm_count));
-        else CK(launch_join_screen<2>(ex->stream, jp, sp, zp, ex->sm_count));
-        LAUNCHED();
-        CK(cudaMemsetAsync(ex->d_scalars + 6, 0, 2 * sizeof(unsigned), ex->stream));
-        sr.retry = (const RetryEntry*)ex->retry.p;
-        sr.retry_count = ex->d_scalars + 5;
-        CK(launch_join_sparse_retry(ex->stream, jp, sr, ex->M, ex->sm_count));
-        LAUNCHED();
-        launches += 5;
-        screened_units += n_all;
-        screened = true;
-      } else {
-        if (sparse_sc_applies(jp, sp)) CK(launch_join_sparse_sc(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
-        else CK(launch_join_sparse(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
-        LAUNCHED();
-        launches++;
-      }
+      const bool thr = sparse_thr(ex->M, pair_hi - pair_lo);
+      if (sparse_sc_applies(jp, sp)) CK(launch_join_sparse_sc(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
+      else CK(launch_join_sparse(ex->stream, jp, sp, ex->M, keep, ex->sm_count, thr));
+      thresholded = thresholded || (thr && !sparse_sc_applies(jp, sp));
+      LAUNCHED();
+      launches++;
     } else {
       jp.pair_begin = p;
       jp.pair_end = pe;
@@ -1920,7 +1835,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ex->ev0, ex->ev1));
     kernel_ms += ms;
-    exact_units += (unsigned long long)ex->h_scalars[4] + ex->h_scalars[5];
+    exact_pairs += (unsigned long long)ex->h_scalars[4] | ((unsigned long long)ex->h_scalars[5] << 32);
     if (ex->h_scalars[0] > cap) {
       // budget overflow: redo this range in safe chunks (growing x8 up to 4M pairs)
       unsigned long long chunk = redo_first;
@@ -2000,9 +1915,8 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     opts->launches = launches;
     opts->precounted = sp.pcnt1 != nullptr;
     opts->split_carrier = kernel == GCRE_KERNEL_SPARSE && sparse_sc_applies(jp, sp);
-    opts->screened = screened ? 1 : 0;
-    opts->exact_units = screened ? exact_units : 0;
-    opts->total_units = screened_units;
+    opts->thresholded = thresholded ? 1 : 0;
+    opts->exact_pairs = exact_pairs;
   }
   return GCRE_OK;
 }

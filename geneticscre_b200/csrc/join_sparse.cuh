@@ -44,17 +44,21 @@ constexpr int WARPS = THREADS / 32;
 constexpr int PB = 64;          // partners per unit
 constexpr int FLUSH_AT = 240;   // carrier slots accumulated in the 8 bit planes before they are flushed into u16 counters
 constexpr int QCAP = 96;        // per-warp queue of filtered partner carriers (drained at 64)
-// Resident CTAs per SM asked of ptxas (= register budget).  Round 1 (32 running maxima per lane in registers) measured on the
-// level-4 join of BASELINE config 3: method 1 best at 8 CTAs (64 registers, 164 B spilled), method 2 at 5 (96 registers).
-// With the thresholded look-ups (no running maxima) both compile to 64 registers without spills: 8 CTAs = 32 warps per SM;
-// method 1 also fits 48 registers (10 CTAs).  Measured choices: profiles/r2_occupancy_variants.txt.
+// Resident CTAs per SM asked of ptxas (= register budget).  Measured on B200 with the level-4 join of BASELINE config 3:
+//   running maxima in registers (THR = false): method 1 best at 8 CTAs (64 registers, a few hundred bytes spilled), method 2 at 5
+//   (96 registers, no spills; 6 CTAs spill);
+//   thresholded look-ups (THR = true): both methods compile to 64 registers without spills -> 8 CTAs = 32 warps per SM
+//   (method 2 at 6 / 7 / 8 CTAs: 17.2 / 16.5 / 16.4 ms; method 1 at 8 / 10 / 12: 12.9 / 12.7 / 12.7 ms, profiles/r2_occupancy_variants.txt).
 #ifndef GCRE_SPARSE_MB2
-#define GCRE_SPARSE_MB2 8
+#define GCRE_SPARSE_MB2 5
 #endif
 #ifndef GCRE_SPARSE_MB1
 #define GCRE_SPARSE_MB1 8
 #endif
-constexpr int min_blocks(int m) { return m == 1 ? GCRE_SPARSE_MB1 : GCRE_SPARSE_MB2; }
+#ifndef GCRE_SPARSE_MB_THR
+#define GCRE_SPARSE_MB_THR 8
+#endif
+constexpr int min_blocks(int m, bool thr) { return thr ? GCRE_SPARSE_MB_THR : (m == 1 ? GCRE_SPARSE_MB1 : GCRE_SPARSE_MB2); }
 }  // namespace sparse
 
 // Carrier-list (CSR) view of a path set: per (row, half) the ascending patient indices of its set bits.
@@ -74,8 +78,6 @@ struct SparseView {
   // [item][perm block][q = 0..3][lane][4] u32 = packed u16 pairs (registers 4q..4q+3 of GCRE_C16_REG) - 2 KB per block
   uint32_t* pcnt = nullptr;
   unsigned long long pcnt_gen = 0;  // exec->mask_gen the table was built for
-  // min | max << 16 over the 32 permutations of every lane of the emitted counts: [item][perm block][lane] (join_screen.cuh)
-  uint32_t* prange = nullptr;
   // rows whose counts / ranges / len / ncase were emitted: a KEEP join over a shard of its upstream rows (multi-GPU: each
   // rank builds only the rows its shard of the next level consumes) fills [emit_lo, emit_hi) only
   unsigned long long emit_lo = 0, emit_hi = 0;
@@ -95,30 +97,8 @@ struct SparseParams {
   uint32_t* pcnt_res;                     // KEEP: where to emit the counts / carrier totals of the kept rows, else null
   uint32_t* len_res;
   uint32_t* ncase_res;
-  uint32_t* prange_res;                   // KEEP: per-lane min | max << 16 of the emitted counts (join_screen.cuh), else null
-  // RETRY kernels (join_screen.cuh): work items are the entries of this list (unit, permutation block, partner mask)
-  const struct RetryEntry* retry;
-  const unsigned* retry_count;
+  unsigned long long* exact_pairs;        // diagnostic (thresholded look-ups): pairs whose exact permutation scores had to be looked up
 };
-
-struct RetryEntry {
-  uint32_t unit;            // absolute unit index
-  uint32_t pb;              // permutation block
-  unsigned long long mask;  // partners of the unit (bit j - j0) that need exact scoring
-};
-
-// min / max over the 32 u16 counts a lane holds in 16 packed registers -> min | max << 16
-__device__ __forceinline__ uint32_t range16(const uint32_t (&v)[16]) {
-  uint32_t mn = __vimin3_u16x2(v[0], v[1], v[2]), mx = __vimax3_u16x2(v[0], v[1], v[2]);
-#pragma unroll
-  for (int i = 3; i < 15; i += 2) {
-    mn = __vimin3_u16x2(mn, v[i], v[i + 1]);
-    mx = __vimax3_u16x2(mx, v[i], v[i + 1]);
-  }
-  mn = __vminu2(mn, v[15]);
-  mx = __vmaxu2(mx, v[15]);
-  return min(mn & 0xffffu, mn >> 16) | (max(mx & 0xffffu, mx >> 16) << 16);
-}
 
 // ---- view construction ----------------------------------------------------------------------------------------------
 // per (row, half): true carrier count and the padded count (multiple of 8) that is prefix-summed into offsets
@@ -281,10 +261,9 @@ __global__ void __launch_bounds__(128) build_precount_kernel(const unsigned long
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // CT = carrier index type of the list views: uint16_t (n <= 65,535) or uint32_t
-// RETRY: the work items are the entries of s.retry - units with a mask of the partners to score, permutation maxima only
-// (true scores, candidates and kept rows were handled by the screening kernel, join_screen.cuh)
-template <int M, bool KEEP, typename CT, bool PC, bool RETRY = false>
-__global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_sparse_kernel(const JoinParams a, const SparseParams s) {
+// THR: thresholded look-ups (below) instead of 32 running maxima per lane in registers
+template <int M, bool KEEP, typename CT, bool PC, bool THR>
+__global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) join_sparse_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse;
   const CT* car0 = static_cast<const CT*>(s.car0);
   const CT* car1 = static_cast<const CT*>(s.car1);
@@ -295,25 +274,39 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
   // method 2: the two halves go through ONE instance of the filter / accumulate / flush code (a rolled loop), their counts
   // parked here for the look-up stage: unrolled per half the kernel was 62 KB of SASS and lost more issue slots to
   // instruction fetch than to memory latency (profiles/r1_sparse_final_full.txt, no_instruction 4.1 vs long_scoreboard 4.0)
-  // method 2 parks the counts of half 0 here while half 1 accumulates (the last half stays in registers for the look-ups)
-  __shared__ uint32_t s_cnt[1][M == 2 ? 16 : 1][THREADS];
+  // method 2: counts parked for the look-up stage.  THR: half 0 only (the last half stays in registers); else both halves
+  __shared__ uint32_t s_cnt[(M == 2 && !THR) ? 2 : 1][M == 2 ? 16 : 1][THREADS];
 
   const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Wp = a.Wp, Iw = a.Iw;  // Iw: words per patient row of pt (a multiple of 32: every lane owns a valid word)
   const int row_words = Wp * M;
-  const unsigned long long n_work = RETRY ? (unsigned long long)__ldg(s.retry_count) : s.n_units * (unsigned long long)s.n_perm_blocks;
+  const unsigned long long n_work = s.n_units * (unsigned long long)s.n_perm_blocks;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint32_t* queue = s_queue[warp];
 
-  // Thresholded look-ups.  The per-permutation maxima live in global memory only (a.perm_max, float bit patterns >= +0, raised
-  // with atomicMax).  A lane keeps ONE float, thr: a lower bound of the current maxima of its 32 permutations (their minimum when
-  // last read - maxima only grow).  A pair's look-ups first only ask "does any permutation score above thr?" (one compare per
-  // look-up, no running-maximum registers); only then - a few times per thousand pairs once the maxima have settled - the pair's
+  // THR = false: 32 running maxima per lane in registers, merged into a.perm_max with one atomicMax per permutation when the
+  // warp changes permutation block or runs out of work.
+  float best[THR ? 1 : 32];
+#pragma unroll
+  for (int b = 0; b < (THR ? 1 : 32); b++) best[b] = 0.0f;
+  auto flush_best = [&](int pb) {
+    const int r0 = (pb * 32 + lane) * 32;
+    if (!THR && r0 < a.Ip) {
+#pragma unroll
+      for (int b = 0; b < (THR ? 1 : 32); b++)
+        if (best[b] > 0.0f) atomicMax(a.perm_max + r0 + b, __float_as_int(best[b]));
+    }
+  };
+  // THR = true: thresholded look-ups.  The per-permutation maxima live in global memory only (a.perm_max, float bit patterns
+  // >= +0, raised with atomicMax).  A lane keeps ONE float, thr: a lower bound of the current maxima of its 32 permutations (their
+  // minimum when last read - maxima only grow).  A pair's look-ups first only ask "does any permutation score above thr?" (one
+  // compare per look-up, no running-maximum registers); only then - about one pair in a hundred on BASELINE config 3 - the pair's
   // exact scores are pushed with atomicMax and thr is re-read.  Method 2 asks the question with round-up f32 copies of its f64
   // table and a round-up add, an upper bound of the exactly rounded f64 sum, and computes the f64 sums only in the rare path.
-  // Compared with 32 running maxima per lane this frees 31 registers (method 2: 96 -> 72, 5 -> 7 CTAs per SM).
+  // This frees 31 registers: method 2 runs at 64 registers / 8 CTAs per SM instead of 96 / 5 (level-4 join 19.3 -> 16.4 ms).  It
+  // pays only on large joins: every warp's first pairs take the exact path (the maxima start at zero), and method 1 - already at
+  // 8 CTAs - loses (11.2 -> 12.9 ms: the compare chain has less instruction-level parallelism than 32 independent maxima).
   float thr = 0.0f;
-  int pb_cur = -1;
   unsigned since_refresh = 0;
   auto load_thr = [&](int pb) -> float {
     const int r0 = (pb * 32 + lane) * 32;
@@ -327,29 +320,27 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     }
     return m;
   };
+  int pb_cur = -1;
 
   while (true) {
     unsigned long long g = 0;
     if (lane == 0) g = atomicAdd(s.work_counter, 1ull);
     g = __shfl_sync(0xffffffffu, g, 0);
     if (g >= n_work) break;
-    unsigned long long retry_mask = ~0ull;
-    int pb;
-    unsigned long long unit;
-    if (RETRY) {
-      const RetryEntry e = s.retry[g];
-      pb = (int)e.pb;
-      unit = e.unit;
-      retry_mask = e.mask;
-    } else {
-      pb = (int)(g / s.n_units);
-      unit = s.unit_begin + (g % s.n_units);
-    }
-    if (pb != pb_cur || (++since_refresh & 7u) == 0u) {  // other warps keep raising the maxima: re-read every 8th unit
-      thr = load_thr(pb);
+    const int pb = (int)(g / s.n_units);
+    const unsigned long long unit = s.unit_begin + (g % s.n_units);
+    if (THR) {
+      if (pb != pb_cur || (++since_refresh & 7u) == 0u) {  // other warps keep raising the maxima: re-read every 8th unit
+        thr = load_thr(pb);
+        pb_cur = pb;
+      }
+    } else if (pb != pb_cur) {
+      if (pb_cur >= 0) flush_best(pb_cur);
+#pragma unroll
+      for (int b = 0; b < (THR ? 1 : 32); b++) best[b] = 0.0f;
       pb_cur = pb;
     }
-    const bool first_pb = !RETRY && (pb == 0);
+    const bool first_pb = (pb == 0);
     const uint32_t idx = s.unit_idx[unit];
     const uint32_t sub = (uint32_t)(unit - s.unit_prefix[idx]);
     const uint32_t cnt_idx = (uint32_t)a.count[idx];
@@ -448,7 +439,6 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     bool base_done = false;
     // ---- partners ----
     for (uint32_t j = j0; j < j1; j++) {
-      if (RETRY && !((retry_mask >> (j - j0)) & 1ull)) continue;
       const uint32_t loc = loc0 + j;
       if (PC && j + 1 < j1) prefetch_partner(loc + 1);
       bool flip = true;
@@ -510,13 +500,11 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
           ncnh = s.ncase1[item] - ncnh;
         }
         if (M == 2) {
-          if (h == 0) {
+          if (h == 0 || !THR) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) s_cnt[0][M == 2 ? i : 0][tid] = c16[i];
-            nd[0] = ndh; ncn[0] = ncnh; pitem[0] = item;
-          } else {
-            nd[M - 1] = ndh; ncn[M - 1] = ncnh; pitem[M - 1] = item;
+            for (int i = 0; i < 16; i++) s_cnt[THR ? 0 : h][M == 2 ? i : 0][tid] = c16[i];
           }
+          if (h == 0) { nd[0] = ndh; ncn[0] = ncnh; pitem[0] = item; } else { nd[M - 1] = ndh; ncn[M - 1] = ncnh; pitem[M - 1] = item; }
         } else {
           nd[0] = ndh;
           ncn[0] = ncnh;
@@ -528,71 +516,138 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
       if (M == 2) empty = empty && nd[M - 1] == 0;
       if (!empty || !base_done) {
         if (empty) base_done = true;
-        if (PC) {
-          // counts = base + P[partner] - overlap, packed u16 pairs (whole-register arithmetic is exact: every final half is a
-          // count in [0, 65535]); finalised in place: half 0 of method 2 in its shared-memory slots, the last half in c16
-          const uint4* P0 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[0] * s.n_perm_blocks + pb) * 4) * 32 + lane;
-          const uint4* P1 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[M - 1] * s.n_perm_blocks + pb) * 4) * 32 + lane;
+        if constexpr (THR) {
+          if (PC) {
+            // counts = base + P[partner] - overlap, packed u16 pairs (whole-register arithmetic is exact: every final half is a
+            // count in [0, 65535]); finalised in place: half 0 of method 2 in its shared-memory slots, the last half in c16
+            const uint4* P0 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[0] * s.n_perm_blocks + pb) * 4) * 32 + lane;
+            const uint4* P1 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[M - 1] * s.n_perm_blocks + pb) * 4) * 32 + lane;
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const uint4 pv = __ldg(P1 + q * 32);
-            const uint32_t pr[4] = {pv.x, pv.y, pv.z, pv.w};
+            for (int q = 0; q < 4; q++) {
+              const uint4 pv = __ldg(P1 + q * 32);
+              const uint32_t pr[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
-            for (int k = 0; k < 4; k++) c16[4 * q + k] = s_base[M - 1][4 * q + k][tid] + pr[k] - c16[4 * q + k];
-            if (M == 2) {
-              const uint4 pw = __ldg(P0 + q * 32);
-              const uint32_t pr0[4] = {pw.x, pw.y, pw.z, pw.w};
+              for (int k = 0; k < 4; k++) c16[4 * q + k] = s_base[M - 1][4 * q + k][tid] + pr[k] - c16[4 * q + k];
+              if (M == 2) {
+                const uint4 pw = __ldg(P0 + q * 32);
+                const uint32_t pr0[4] = {pw.x, pw.y, pw.z, pw.w};
 #pragma unroll
-              for (int k = 0; k < 4; k++)
-                s_cnt[0][M == 2 ? 4 * q + k : 0][tid] = s_base[0][4 * q + k][tid] + pr0[k] - s_cnt[0][M == 2 ? 4 * q + k : 0][tid];
+                for (int k = 0; k < 4; k++)
+                  s_cnt[0][M == 2 ? 4 * q + k : 0][tid] = s_base[0][4 * q + k][tid] + pr0[k] - s_cnt[0][M == 2 ? 4 * q + k : 0][tid];
+              }
             }
           }
-        }
-        // final counts of permutation bit b: register GCRE_C16_REG(b), half GCRE_C16_HI(b); the last half (method 1: the only
-        // one) is in c16, half 0 of method 2 in shared memory
-        bool hit = false;
-        if (M == 1) {
-          const float* row = a.diagF + diag_base(t0[0] + nd[0]);
+          // final counts of permutation bit b: register GCRE_C16_REG(b), half GCRE_C16_HI(b); the last half (method 1: the only
+          // one) is in c16, half 0 of method 2 in shared memory
+          bool hit = false;
+          if (M == 1) {
+            const float* row = a.diagF + diag_base(t0[0] + nd[0]);
 #pragma unroll
-          for (int b = 0; b < 32; b++) {
-            const uint32_t v = c16[GCRE_C16_REG(b)];
-            const uint32_t c = GCRE_C16_HI(b) ? (v >> 16) : (v & 0xffffu);
-            hit |= __ldg(row + c) > thr;
+            for (int b = 0; b < 32; b++) {
+              const uint32_t v = c16[GCRE_C16_REG(b)];
+              const uint32_t c = GCRE_C16_HI(b) ? (v >> 16) : (v & 0xffffu);
+              hit |= __ldg(row + c) > thr;
+            }
+          } else {
+            // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
+            const unsigned tn = t0[M - 1] + nd[M - 1];
+            const float* frp = a.diagFM + diag_base(t0[0] + nd[0]);
+            const float* frn = a.diagFM + diag_base(tn) + tn;
+#pragma unroll
+            for (int b = 0; b < 32; b++) {
+              const uint32_t vp = s_cnt[0][M == 2 ? GCRE_C16_REG(b) : 0][tid], vn = c16[GCRE_C16_REG(b)];
+              const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
+              const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
+              hit |= __fadd_ru(__ldg(frp + cp), __ldg(frn - cn)) > thr;  // >= the exactly rounded f64 sum
+            }
+          }
+          if (__any_sync(0xffffffffu, hit)) {
+            // rare: exact scores of the pair -> global maxima.  A rolled loop (small code, no register pressure on the common path):
+            // the last half's counts are copied to a dynamically indexed local array (thread-private memory, touched only here)
+            uint32_t lc[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) lc[i] = c16[i];
+            const int r0 = (pb * 32 + lane) * 32;
+            const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
+#pragma unroll 1
+            for (int b = 0; b < 32; b++) {
+              const int reg = GCRE_C16_REG(b), sh = GCRE_C16_HI(b) * 16;
+              float p;
+              if (M == 1) {
+                p = __ldg(a.diagF + diag_base(tp) + ((lc[reg] >> sh) & 0xffffu));
+              } else {
+                const uint32_t cp = (s_cnt[0][M == 2 ? reg : 0][tid] >> sh) & 0xffffu, cn = (lc[reg] >> sh) & 0xffffu;
+                p = __double2float_rn(__ldg(a.diagDM + diag_base(tp) + cp) + __ldg(a.diagDM + diag_base(tn) + tn - cn));
+              }
+              if (p > thr) atomicMax(a.perm_max + r0 + b, __float_as_int(p));
+            }
+            thr = load_thr(pb);
           }
         } else {
-          // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
-          const unsigned tn = t0[M - 1] + nd[M - 1];
-          const float* frp = a.diagFM + diag_base(t0[0] + nd[0]);
-          const float* frn = a.diagFM + diag_base(tn) + tn;
-#pragma unroll
-          for (int b = 0; b < 32; b++) {
-            const uint32_t vp = s_cnt[0][M == 2 ? GCRE_C16_REG(b) : 0][tid], vn = c16[GCRE_C16_REG(b)];
-            const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
-            const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
-            hit |= __fadd_ru(__ldg(frp + cp), __ldg(frn - cn)) > thr;  // >= the exactly rounded f64 sum
-          }
-        }
-        if (__any_sync(0xffffffffu, hit)) {
-          // rare: exact scores of the pair -> global maxima.  A rolled loop (small code, no register pressure on the common path):
-          // the last half's counts are copied to a dynamically indexed local array (thread-private memory, touched only here)
-          uint32_t lc[16];
-#pragma unroll
-          for (int i = 0; i < 16; i++) lc[i] = c16[i];
-          const int r0 = (pb * 32 + lane) * 32;
-          const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
-#pragma unroll 1
-          for (int b = 0; b < 32; b++) {
-            const int reg = GCRE_C16_REG(b), sh = GCRE_C16_HI(b) * 16;
-            float p;
+          if (PC) {
+            // counts = base + P[partner] - overlap, packed u16 pairs (whole-register arithmetic is exact: every final half
+            // is a count in [0, 65535]); register i holds permutation bits b = ((i & 1) * 2 + hf) * 8 + (i >> 1), hf = 0, 1
+            const uint4* P0 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[0] * s.n_perm_blocks + pb) * 4) * 32 + lane;
             if (M == 1) {
-              p = __ldg(a.diagF + diag_base(tp) + ((lc[reg] >> sh) & 0xffffu));
+              const unsigned total = t0[0] + nd[0];
+              const float* row = a.diagF + diag_base(total);
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const uint4 pv = __ldg(P0 + q * 32);
+                const uint32_t pr[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const int i = 4 * q + k;
+                  const uint32_t v = s_base[0][i][tid] + pr[k] - c16[i];
+                  best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __ldg(row + (v & 0xffffu)));
+                  best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __ldg(row + (v >> 16)));
+                }
+              }
             } else {
-              const uint32_t cp = (s_cnt[0][M == 2 ? reg : 0][tid] >> sh) & 0xffffu, cn = (lc[reg] >> sh) & 0xffffu;
-              p = __double2float_rn(__ldg(a.diagDM + diag_base(tp) + cp) + __ldg(a.diagDM + diag_base(tn) + tn - cn));
+              const uint4* P1 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[M - 1] * s.n_perm_blocks + pb) * 4) * 32 + lane;
+              const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
+              const double* rowp = a.diagDM + diag_base(tp);
+              const double* rown = a.diagDM + diag_base(tn) + tn;
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const uint4 pvp = __ldg(P0 + q * 32), pvn = __ldg(P1 + q * 32);
+                const uint32_t prp[4] = {pvp.x, pvp.y, pvp.z, pvp.w}, prn[4] = {pvn.x, pvn.y, pvn.z, pvn.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const int i = 4 * q + k;
+                  const uint32_t vp = s_base[0][i][tid] + prp[k] - s_cnt[0][M == 2 ? i : 0][tid];
+                  const uint32_t vn = s_base[M - 1][i][tid] + prn[k] - s_cnt[M == 2 ? 1 : 0][M == 2 ? i : 0][tid];
+                  // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
+                  const double vlo = __ldg(rowp + (vp & 0xffffu)) + __ldg(rown - (vn & 0xffffu));
+                  const double vhi = __ldg(rowp + (vp >> 16)) + __ldg(rown - (vn >> 16));
+                  best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __double2float_rn(vlo));
+                  best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __double2float_rn(vhi));
+                }
+              }
             }
-            if (p > thr) atomicMax(a.perm_max + r0 + b, __float_as_int(p));
+          } else if (M == 1) {
+            const unsigned total = t0[0] + nd[0];
+            const float* row = a.diagF + diag_base(total);
+#pragma unroll
+            for (int b = 0; b < 32; b++) {
+              const uint32_t v = c16[GCRE_C16_REG(b)];
+              const uint32_t c = GCRE_C16_HI(b) ? (v >> 16) : (v & 0xffffu);
+              best[b] = fmaxf(best[b], __ldg(row + c));
+            }
+          } else {
+            const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
+            const double* rowp = a.diagDM + diag_base(tp);
+            const double* rown = a.diagDM + diag_base(tn) + tn;
+#pragma unroll
+            for (int b = 0; b < 32; b++) {
+              const uint32_t vp = s_cnt[0][M == 2 ? GCRE_C16_REG(b) : 0][tid], vn = s_cnt[M == 2 ? 1 : 0][M == 2 ? GCRE_C16_REG(b) : 0][tid];
+              const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
+              const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
+              // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
+              const double v = __ldg(rowp + cp) + __ldg(rown - cn);
+              best[b] = fmaxf(best[b], __double2float_rn(v));
+            }
           }
-          thr = load_thr(pb);
         }
       }
 
@@ -602,13 +657,11 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
 #pragma unroll
         for (int h = 0; h < M; h++) {
           uint4* out = reinterpret_cast<uint4*>(s.pcnt_res) + (((r * M + h) * s.n_perm_blocks + pb) * 4) * 32 + lane;
-          uint32_t v16[16];  // the last half is in registers, half 0 of method 2 in shared memory
+          uint32_t v16[16];  // method 1 / THR: the last half is in registers; method 2: parked halves in shared memory
 #pragma unroll
-          for (int i = 0; i < 16; i++) v16[i] = (h == M - 1) ? c16[i] : s_cnt[0][M == 2 ? i : 0][tid];
+          for (int i = 0; i < 16; i++) v16[i] = (M == 1 || (THR && h == M - 1)) ? c16[i] : s_cnt[(M == 2 && !THR) ? h : 0][M == 2 ? i : 0][tid];
 #pragma unroll
           for (int q = 0; q < 4; q++) __stcs(out + q * 32, make_uint4(v16[4 * q], v16[4 * q + 1], v16[4 * q + 2], v16[4 * q + 3]));
-          // the range of the lane's 32 counts: all the screening kernel of the next level reads of them
-          s.prange_res[((r * M + h) * s.n_perm_blocks + pb) * 32 + lane] = range16(v16);
           if (first_pb && lane == 0) {
             s.len_res[r * M + h] = t0[h == 0 ? 0 : M - 1] + nd[h == 0 ? 0 : M - 1];
             s.ncase_res[r * M + h] = nc0[h == 0 ? 0 : M - 1] + ncn[h == 0 ? 0 : M - 1];
@@ -681,6 +734,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M)) join_s
     }
     __syncwarp();
   }
+  if (!THR && pb_cur >= 0) flush_best(pb_cur);
 }
 
 // u32 carrier indices when n (which is also the sentinel index) does not fit u16; GCRE_TEST_WIDE_CARRIERS=1 (test hook)
@@ -708,45 +762,45 @@ static inline double sparse_pair_ns(int n_perm_blocks, int M, double new_carrier
   return n_perm_blocks * ((M == 1 ? 1.5 : 2.0) + (M == 1 ? 0.075 : 0.1) * new_carriers_per_pair);
 }
 
-template <int M, bool KEEP, bool PC>
+// Thresholded look-ups pay on large method-2 joins only (see the kernel); GCRE_THR=0 / 1 forces them off / on for every join
+static inline bool sparse_thr(int M, unsigned long long n_pairs) {
+  if (const char* e = std::getenv("GCRE_THR")) {
+    if (*e == '0' || *e == '1') return *e == '1';
+  }
+  return M == 2 && n_pairs >= (1ull << 20);
+}
+
+template <int M, bool KEEP, bool PC, bool THR>
 static inline void launch_sparse_ct(unsigned grid, cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, bool wide) {
-  if (wide) join_sparse_kernel<M, KEEP, uint32_t, PC><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
-  else join_sparse_kernel<M, KEEP, uint16_t, PC><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+  if (wide) join_sparse_kernel<M, KEEP, uint32_t, PC, THR><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+  else join_sparse_kernel<M, KEEP, uint16_t, PC, THR><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
 }
 
-template <int M, bool KEEP>
+template <int M, bool KEEP, bool THR>
 static inline void launch_sparse_pc(unsigned grid, cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, bool wide) {
-  if (sp.pcnt1) launch_sparse_ct<M, KEEP, true>(grid, stream, jp, sp, wide);
-  else launch_sparse_ct<M, KEEP, false>(grid, stream, jp, sp, wide);
+  if (sp.pcnt1) launch_sparse_ct<M, KEEP, true, THR>(grid, stream, jp, sp, wide);
+  else launch_sparse_ct<M, KEEP, false, THR>(grid, stream, jp, sp, wide);
 }
 
-// sp.pcnt1 != null selects the pre-counted-partner kernels
-static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count) {
+template <int M, bool THR>
+static inline void launch_sparse_keep(unsigned grid, cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, bool wide, bool keep) {
+  if (keep) launch_sparse_pc<M, true, THR>(grid, stream, jp, sp, wide);
+  else launch_sparse_pc<M, false, THR>(grid, stream, jp, sp, wide);
+}
+
+// sp.pcnt1 != null selects the pre-counted-partner kernels; `thr` the thresholded look-ups
+static inline cudaError_t launch_join_sparse(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count, bool thr) {
   const unsigned long long n_work = sp.n_units * (unsigned long long)sp.n_perm_blocks;
   if (n_work == 0) return cudaSuccess;
   const unsigned long long want = (n_work + sparse::WARPS - 1) / sparse::WARPS;
-  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * sparse::min_blocks(M));
+  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * sparse::min_blocks(M, thr));
   const bool wide = sparse_wide(sp.n);
   if (M == 1) {
-    if (keep) launch_sparse_pc<1, true>(grid, stream, jp, sp, wide);
-    else launch_sparse_pc<1, false>(grid, stream, jp, sp, wide);
+    if (thr) launch_sparse_keep<1, true>(grid, stream, jp, sp, wide, keep);
+    else launch_sparse_keep<1, false>(grid, stream, jp, sp, wide, keep);
   } else {
-    if (keep) launch_sparse_pc<2, true>(grid, stream, jp, sp, wide);
-    else launch_sparse_pc<2, false>(grid, stream, jp, sp, wide);
-  }
-  return cudaGetLastError();
-}
-
-// exact scoring of the entries of sp.retry (permutation maxima only); the entry count is read on the device
-static inline cudaError_t launch_join_sparse_retry(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, int sm_count) {
-  const unsigned grid = (unsigned)sm_count * sparse::min_blocks(M);
-  const bool wide = sparse_wide(sp.n);
-  if (M == 1) {
-    if (wide) join_sparse_kernel<1, false, uint32_t, false, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
-    else join_sparse_kernel<1, false, uint16_t, false, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
-  } else {
-    if (wide) join_sparse_kernel<2, false, uint32_t, false, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
-    else join_sparse_kernel<2, false, uint16_t, false, true><<<grid, sparse::THREADS, 0, stream>>>(jp, sp);
+    if (thr) launch_sparse_keep<2, true>(grid, stream, jp, sp, wide, keep);
+    else launch_sparse_keep<2, false>(grid, stream, jp, sp, wide, keep);
   }
   return cudaGetLastError();
 }

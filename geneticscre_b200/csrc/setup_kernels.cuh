@@ -130,8 +130,8 @@ __global__ void masks_to_patient_major_kernel(const uint64_t* __restrict__ masks
   if (warp >= (long long)Iw * n_cblk) return;
   const int w = (int)(warp / n_cblk);   // perm word
   const int cb = (int)(warp % n_cblk);  // block of 32 patients
-  // slots beyond the requested permutations hold copies of real ones (r mod iters): their counts then lie inside the range of
-  // real counts, which the screening kernel (join_screen.cuh) relies on; their maxima are never read
+  // slots beyond the requested permutations hold copies of real ones (r mod iters): they score like real permutations, so a
+  // lane's threshold (thresholded look-ups, join_sparse.cuh) is not pinned at zero by padding; their maxima are never read
   const int r = (iters > 0) ? (w * 32 + lane) % iters : 0;
   uint32_t mine = 0;  // 32 patient bits of perm r
   if (iters > 0) {

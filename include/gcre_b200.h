@@ -85,10 +85,11 @@ typedef struct {
   int32_t launches;         /* out: kernel launches made by this call */
   int32_t precounted;       /* out: 1 when the sparse kernel ran in its pre-counted-partner form (join_sparse.cuh) */
   int32_t split_carrier;    /* out: 1 when the <= 512-permutation form of the sparse kernel ran (join_sparse_sc.cuh) */
-  int32_t screened;         /* out: 1 when the range-bound screening kernel ran ahead of the exact one (join_screen.cuh) */
+  int32_t thresholded;      /* out: 1 when the sparse kernel ran with thresholded look-ups (join_sparse.cuh: large method-2 joins) */
   int32_t reserved;
-  uint64_t exact_units;     /* out: (unit, permutation block) work items the exact kernel scored for a screened join: seed + retries */
-  uint64_t total_units;     /* out: (unit, permutation block) work items of the join */
+  uint64_t exact_pairs;     /* out: with thresholded look-ups, the pairs (per 1,024-permutation block) whose exact permutation scores
+                               had to be looked up; every other pair was ruled out by one compare per look-up */
+  uint64_t reserved2;
 } gcre_join_opts;
 
 /* One split of a reported path for the decorated p-value (R/DecoratedPvalue.R:198-304). */

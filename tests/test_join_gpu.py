@@ -25,16 +25,16 @@ class _NoSplit(int):
     one-word-per-lane kernel - delta form, counts handed from level to level - runs on the small shapes too."""
 
 
-class _Screen(_NoSplit):
-    """As _NoSplit, plus the range-bound screening kernel (join_screen.cuh) forced onto joins of any size
-    (GCRE_TEST_SCREEN=1; the seed pass takes every 3rd unit so that seed, screening and retry passes all see work)."""
+class _Thresholded(_NoSplit):
+    """As _NoSplit, with the thresholded look-ups (join_sparse.cuh, THR kernels) forced onto joins of any size and both methods
+    (GCRE_THR=1); every other variant forces them off (GCRE_THR=0), so both look-up stages run on every shape."""
 
 
 SPARSE_PC = _Precount(_lib.KERNEL_SPARSE)
 SPARSE_NOSPLIT = _NoSplit(_lib.KERNEL_SPARSE)
-SPARSE_SCREEN = _Screen(_lib.KERNEL_SPARSE)
+SPARSE_THR = _Thresholded(_lib.KERNEL_SPARSE)
 KERNELS = [pytest.param(_lib.KERNEL_DENSE, id="dense"), pytest.param(_lib.KERNEL_SPARSE, id="sparse"), pytest.param(SPARSE_PC, id="sparse_pc"),
-           pytest.param(SPARSE_NOSPLIT, id="sparse_nosplit"), pytest.param(SPARSE_SCREEN, id="sparse_screen")]
+           pytest.param(SPARSE_NOSPLIT, id="sparse_nosplit"), pytest.param(SPARSE_THR, id="sparse_thr")]
 PC_MODES = [pytest.param("0", id="delta"), pytest.param("1", id="precount")]
 
 
@@ -48,11 +48,7 @@ def _precount_mode(request, monkeypatch):
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", "0")
     if isinstance(k, _NoSplit):
         monkeypatch.setenv("GCRE_TEST_NO_SPLIT", "1")
-    if isinstance(k, _Screen):
-        monkeypatch.setenv("GCRE_TEST_SCREEN", "1")
-        monkeypatch.setenv("GCRE_TEST_SCREEN_STRIDE", "3")
-    else:
-        monkeypatch.setenv("GCRE_SCREEN", "0")
+    monkeypatch.setenv("GCRE_THR", "1" if isinstance(k, _Thresholded) else "0")
     if "pc" in params:
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", params["pc"])
 
@@ -114,8 +110,12 @@ def test_schedule_matches_oracle(engine, oracles, method, shape, kernel):
             assert got[lvl].info["precounted"] == isinstance(kernel, _Precount), "GCRE_TEST_PRECOUNT must select the kernel form"
         if kernel == _lib.KERNEL_SPARSE and not isinstance(kernel, _Precount) and w.net.levels[lvl].n_pairs > 0:
             assert got[lvl].info["split_carrier"] == (perms <= 512 and not isinstance(kernel, _NoSplit)), "<= 512 permutations run the split-carrier form"
-        if w.net.levels[lvl].n_pairs > 0 and lvl in ("4", "5"):
-            assert got[lvl].info["screened"] == isinstance(kernel, _Screen), "levels 4 and 5 are the screened joins (upstream rows carry counts + ranges)"
+        if kernel == _lib.KERNEL_SPARSE and w.net.levels[lvl].n_pairs > 0 and not got[lvl].info["split_carrier"]:
+            assert got[lvl].info["thresholded"] == isinstance(kernel, _Thresholded), "GCRE_THR must select the look-up stage"
+            if isinstance(kernel, _Thresholded):
+                # the maxima start at zero: at least the first pair of a warp takes the exact path; never more pairs than exist
+                blocks = (max(perms, 1) + 1023) // 1024
+                assert 0 < got[lvl].info["exact_pairs"] <= w.net.levels[lvl].n_pairs * blocks
 
 
 @pytest.mark.parametrize("pc", PC_MODES)

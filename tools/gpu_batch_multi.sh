@@ -6,7 +6,7 @@ OUT=gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 nproc > $OUT/r2_box_n$N.txt; free -g | head -2 >> $OUT/r2_box_n$N.txt; nvidia-smi -L >> $OUT/r2_box_n$N.txt
 if [ "$N" = "2" ]; then
-  python -m pytest tests/test_nccl_gpu.py tests/test_dropin_harness_gpu.py tests/test_cpp_layer_gpu.py -q > $OUT/r2_gputest_n2.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_gputest_n2.log
+  python -m pytest tests -m gpu -q > $OUT/r2_gputest_n2.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_gputest_n2.log
 fi
 # BASELINE config 3 on N GPUs: one block of 1,000 permutations per GPU (weak), plus the fixed job row-sharded (`strong` object) and both parity checks
 $TR bench.py --gpus $N --steps 10 --warmup 3 > $OUT/r2_bench_n$N.json 2> $OUT/r2_bench_n$N.err; echo "rc=$?" >> $OUT/r2_bench_n$N.err
