@@ -567,6 +567,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
             uint32_t lc[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) lc[i] = c16[i];
+            if (lane == 0) atomicAdd(s.exact_pairs, 1ull);  // diagnostic
             const int r0 = (pb * 32 + lane) * 32;
             const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
 #pragma unroll 1

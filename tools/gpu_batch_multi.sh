@@ -19,4 +19,4 @@ if [ "$N" = "8" ]; then
     $TR bench.py --gpus $N --n-cases 25000 --n-ctrls 25000 --n-perms $P --steps 2 --warmup 3 --no-e2e --no-strong > $OUT/r2_cfg5_n8_p$P.json 2> $OUT/r2_cfg5_n8_p$P.err; echo "rc=$?" >> $OUT/r2_cfg5_n8_p$P.err
   done
 fi
-tail -2 $OUT/r2_bench_n$N.err $OUT/r2_cfg4_n$N.err
+for f in $OUT/r2_bench_n$N.err $OUT/r2_cfg4_n$N.err; do tail -n 2 $f; done
