@@ -13,12 +13,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --metrics $M --clock-control none -k regex:join_ -c 60 --csv --log-file $OUT/r2_counts_cfg3.csv $B > $OUT/r2_ncu_counts_cfg3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:join_sparse_kernel -c 10 -o $OUT/r2_final_full \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $OUT/r2_ncu_full.log 2>&1
-# variant: exact path compares candidates with the current maxima before the atomic (default policy, and thresholded everywhere)
-for V in v2c v4 v5; do
-  GCRE_B200_LIB=$PWD/build_variants/lib_$V.so python -m pytest tests/test_join_gpu.py tests/test_fullsize_gpu.py -q -x -k "schedule_matches_oracle or golden or many_permutations or fullsize or agree or compose or first_rows" > $OUT/r2_gputest_$V.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_gputest_$V.log
-  GCRE_B200_LIB=$PWD/build_variants/lib_$V.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/r2_bench_$V.json 2> $OUT/r2_bench_$V.err
-  GCRE_THR=1 GCRE_B200_LIB=$PWD/build_variants/lib_$V.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/r2_bench_${V}_thr1.json 2> $OUT/r2_bench_${V}_thr1.err
-done
 # other BASELINE shapes with this build
 python bench.py --n-perms 100 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/r2_bench_config3_p100.json 2> $OUT/r2_bench_config3_p100.err
 python bench.py --path-length 5 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/r2_bench_config3_len5.json 2> $OUT/r2_bench_config3_len5.err
