@@ -222,6 +222,15 @@ __device__ __forceinline__ void load8(const uint32_t* p, uint32_t (&c)[8]) {
   c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
 }
 
+// base + 4 * word_offset with the base held as a 64-bit register pair: LEA + LEA.HI.X (ptxas strength-reduces the mad.wide).  Left
+// to the compiler, `pt_lane + off` costs IADD3 + IMAD.X + LEA + LEA.HI.X per gather - four ALU-pipe instructions, and the ALU pipe
+// is the busiest one in these kernels.
+__device__ __forceinline__ const uint32_t* word_ptr(const uint32_t* base, uint32_t word_offset) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(word_offset), "l"(base));
+  return reinterpret_cast<const uint32_t*>(r);
+}
+
 // Pre-count table of a path set (see the header): one warp per (item, permutation block).
 template <typename CT>
 __global__ void __launch_bounds__(128) build_precount_kernel(const unsigned long long* __restrict__ off, const CT* __restrict__ car, long long n_items, int n_perm_blocks,
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(128) build_precount_kernel(const unsigned long
     uint32_t c[8], x[8];
     load8(car + o + i, c);
 #pragma unroll
-    for (int q = 0; q < 8; q++) x[q] = __ldg(pt_lane + c[q] * (uint32_t)Iw);
+    for (int q = 0; q < 8; q++) x[q] = __ldg(word_ptr(pt_lane, c[q] * (uint32_t)Iw));
     hs8(pl, x);
     inbatch += 8;
     if (inbatch > sparse::FLUSH_AT || i + 8 >= plen) {
@@ -303,9 +312,9 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
   // compare per look-up, no running-maximum registers); only then - about one pair in a hundred on BASELINE config 3 - the pair's
   // exact scores are pushed with atomicMax and thr is re-read.  Method 2 asks the question with round-up f32 copies of its f64
   // table and a round-up add, an upper bound of the exactly rounded f64 sum, and computes the f64 sums only in the rare path.
-  // This frees 31 registers: method 2 runs at 64 registers / 8 CTAs per SM instead of 96 / 5 (level-4 join 19.3 -> 16.4 ms).  It
-  // pays only on large joins: every warp's first pairs take the exact path (the maxima start at zero), and method 1 - already at
-  // 8 CTAs - loses (11.2 -> 12.9 ms: the compare chain has less instruction-level parallelism than 32 independent maxima).
+  // This frees 31 registers: method 2 runs at 64 registers / 8 CTAs per SM instead of 96 / 5 (level-4 join of BASELINE config 3
+  // 19.3 -> 15.0 ms, 2.4 % of the pairs take the exact path).  Method 1 - already at 8 CTAs - does not gain (10.8 ms with running
+  // maxima, 11.1 thresholded), nor do small joins (every warp's first pairs take the exact path: the maxima start at zero).
   float thr = 0.0f;
   unsigned since_refresh = 0;
   auto load_thr = [&](int pb) -> float {
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
       uint32_t c[8], x[8];
       load8(lst8, c);
 #pragma unroll
-      for (int q = 0; q < 8; q++) x[q] = __ldg(pt_lane + c[q] * (uint32_t)Iw);
+      for (int q = 0; q < 8; q++) x[q] = __ldg(word_ptr(pt_lane, c[q] * (uint32_t)Iw));
       hs8(pl, x);
       inbatch += 8;
       inreal += 8;
@@ -384,14 +393,14 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
     // (keeping a second group of gathers in flight while the first is added - method 2 has the registers - gained < 1 %)
     auto gather8 = [&](uint32_t (&x)[8], const uint32_t* q8) {
       const uint4 lo = *reinterpret_cast<const uint4*>(q8), hi = *reinterpret_cast<const uint4*>(q8 + 4);
-      x[0] = __ldg(pt_lane + lo.x);
-      x[1] = __ldg(pt_lane + lo.y);
-      x[2] = __ldg(pt_lane + lo.z);
-      x[3] = __ldg(pt_lane + lo.w);
-      x[4] = __ldg(pt_lane + hi.x);
-      x[5] = __ldg(pt_lane + hi.y);
-      x[6] = __ldg(pt_lane + hi.z);
-      x[7] = __ldg(pt_lane + hi.w);
+      x[0] = __ldg(word_ptr(pt_lane, lo.x));
+      x[1] = __ldg(word_ptr(pt_lane, lo.y));
+      x[2] = __ldg(word_ptr(pt_lane, lo.z));
+      x[3] = __ldg(word_ptr(pt_lane, lo.w));
+      x[4] = __ldg(word_ptr(pt_lane, hi.x));
+      x[5] = __ldg(word_ptr(pt_lane, hi.y));
+      x[6] = __ldg(word_ptr(pt_lane, hi.z));
+      x[7] = __ldg(word_ptr(pt_lane, hi.w));
     };
     auto acc8 = [&](uint32_t (&c16)[16], const uint32_t (&x)[8], int real, bool last) {
       hs8(pl, x);
@@ -580,7 +589,9 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
                 const uint32_t cp = (s_cnt[0][M == 2 ? reg : 0][tid] >> sh) & 0xffffu, cn = (lc[reg] >> sh) & 0xffffu;
                 p = __double2float_rn(__ldg(a.diagDM + diag_base(tp) + cp) + __ldg(a.diagDM + diag_base(tn) + tn - cn));
               }
-              if (p > thr) atomicMax(a.perm_max + r0 + b, __float_as_int(p));
+              // candidates only (p above the lane's bound) are compared with the permutation's CURRENT maximum, read past L1: an
+              // atomic only for a genuine record (at a cold start every p beats the zero bound - 1,024 atomics per warp otherwise)
+              if (p > thr && p > __int_as_float(__ldcg(a.perm_max + r0 + b))) atomicMax(a.perm_max + r0 + b, __float_as_int(p));
             }
             thr = load_thr(pb);
           }
