@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
           uint32_t c[8];
           load8(lst0 + i + sub * 8, c);
 #pragma unroll
-          for (int q = 0; q < 8; q++) x[q] = __ldg(pt_lane + c[q] * (uint32_t)Iw);
+          for (int q = 0; q < 8; q++) x[q] = __ldg(word_ptr(pt_lane, c[q] * (uint32_t)Iw));
         } else {
 #pragma unroll
           for (int q = 0; q < 8; q++) x[q] = 0u;
@@ -215,14 +215,14 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
             __syncwarp();
             uint32_t x[8];
             const uint4 lo = *reinterpret_cast<const uint4*>(queue + sub * 8), hi = *reinterpret_cast<const uint4*>(queue + sub * 8 + 4);
-            x[0] = __ldg(pt_lane + lo.x);
-            x[1] = __ldg(pt_lane + lo.y);
-            x[2] = __ldg(pt_lane + lo.z);
-            x[3] = __ldg(pt_lane + lo.w);
-            x[4] = __ldg(pt_lane + hi.x);
-            x[5] = __ldg(pt_lane + hi.y);
-            x[6] = __ldg(pt_lane + hi.z);
-            x[7] = __ldg(pt_lane + hi.w);
+            x[0] = __ldg(word_ptr(pt_lane, lo.x));
+            x[1] = __ldg(word_ptr(pt_lane, lo.y));
+            x[2] = __ldg(word_ptr(pt_lane, lo.z));
+            x[3] = __ldg(word_ptr(pt_lane, lo.w));
+            x[4] = __ldg(word_ptr(pt_lane, hi.x));
+            x[5] = __ldg(word_ptr(pt_lane, hi.y));
+            x[6] = __ldg(word_ptr(pt_lane, hi.z));
+            x[7] = __ldg(word_ptr(pt_lane, hi.w));
             const uint32_t rem = qn - real;                      // < 32 entries waiting behind the drained batch
             acc8(c16, x, (int)((real + G - 1) / G), last_chunk && rem == 0);
             // they move to the front: the slot layout is per batch, so whole batches are copied as they are

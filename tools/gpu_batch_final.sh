@@ -7,6 +7,7 @@ M="gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__byt
 python -m pytest tests -m gpu -q > $OUT/r2_gputest_final.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_gputest_final.log
 python bench.py --steps 20 --warmup 5 > $OUT/r2_bench_n1.json 2> $OUT/r2_bench_n1.err; echo "rc=$?" >> $OUT/r2_bench_n1.err
 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/r2_bench_reference_arm.json 2> $OUT/r2_bench_reference_arm.err; echo "rc=$?" >> $OUT/r2_bench_reference_arm.err
+GCRE_BENCH_DEBUG=1 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --e2e-steps 6 > $OUT/r2_e2e_debug.json 2> $OUT/r2_e2e_debug.err
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
 $B > $OUT/r2_prof_plain.json 2> $OUT/r2_prof_plain.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/r2_step_launches.csv $B > $OUT/r2_ncu_launches.log 2>&1
