@@ -419,9 +419,9 @@ def run_reference_arm(a):
     w, _ = make_workload(a)
     arm = ReferenceArm(w, a)
     try:
-        # K + W bounded samples inside ~3 minutes: per-sample join time per method, on top of ~3 s of worker set-up per
-        # method-2 worker (value table, masks, levels 1-3)
-        per_method_s = max(1.0, min(a.cpu_seconds, 90.0 / max(a.steps + a.warmup, 1) / 2))
+        # K + W bounded samples inside ~3 minutes for the driver's --steps 20 --warmup 5: ~1.2 s of join time per method and sample,
+        # on top of method 2's ~1 s fixed cost per join and ~6 s of worker set-up (value table, masks, levels 1-3) every few joins
+        per_method_s = max(0.5, min(a.cpu_seconds, 60.0 / max(a.steps + a.warmup, 1) / 2))
         vals = []
         for i in range(a.warmup + a.steps):
             r = arm.sample(per_method_s)

@@ -230,6 +230,18 @@ __device__ __forceinline__ const uint32_t* word_ptr(const uint32_t* base, uint32
   asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(word_offset), "l"(base));
   return reinterpret_cast<const uint32_t*>(r);
 }
+// the same for the look-up tables: element `index` of a row held as a 64-bit register pair (the compiler otherwise keeps the table
+// base and the row offset in uniform registers and spends IADD3 + IMAD.X + LEA + LEA.HI.X on every look-up)
+__device__ __forceinline__ float lookup_f32(const float* row, uint32_t index) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(index), "l"(row));
+  return __ldg(reinterpret_cast<const float*>(r));
+}
+__device__ __forceinline__ double lookup_f64(const double* row, uint32_t index) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(r) : "r"(index), "l"(row));
+  return __ldg(reinterpret_cast<const double*>(r));
+}
 
 // Pre-count table of a path set (see the header): one warp per (item, permutation block).
 template <typename CT>
@@ -555,19 +567,19 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
             for (int b = 0; b < 32; b++) {
               const uint32_t v = c16[GCRE_C16_REG(b)];
               const uint32_t c = GCRE_C16_HI(b) ? (v >> 16) : (v & 0xffffu);
-              hit |= __ldg(row + c) > thr;
+              hit |= lookup_f32(row, c) > thr;
             }
           } else {
             // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
             const unsigned tn = t0[M - 1] + nd[M - 1];
             const float* frp = a.diagFM + diag_base(t0[0] + nd[0]);
-            const float* frn = a.diagFM + diag_base(tn) + tn;
+            const float* frn = a.diagFM + diag_base(tn);  // indexed by tn - cn
 #pragma unroll
             for (int b = 0; b < 32; b++) {
               const uint32_t vp = s_cnt[0][M == 2 ? GCRE_C16_REG(b) : 0][tid], vn = c16[GCRE_C16_REG(b)];
               const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
               const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
-              hit |= __fadd_ru(__ldg(frp + cp), __ldg(frn - cn)) > thr;  // >= the exactly rounded f64 sum
+              hit |= __fadd_ru(lookup_f32(frp, cp), lookup_f32(frn, tn - cn)) > thr;  // >= the exactly rounded f64 sum
             }
           }
           if (__any_sync(0xffffffffu, hit)) {
@@ -611,15 +623,15 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
                 for (int k = 0; k < 4; k++) {
                   const int i = 4 * q + k;
                   const uint32_t v = s_base[0][i][tid] + pr[k] - c16[i];
-                  best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __ldg(row + (v & 0xffffu)));
-                  best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __ldg(row + (v >> 16)));
+                  best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], lookup_f32(row, v & 0xffffu));
+                  best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], lookup_f32(row, v >> 16));
                 }
               }
             } else {
               const uint4* P1 = reinterpret_cast<const uint4*>(s.pcnt1) + ((pitem[M - 1] * s.n_perm_blocks + pb) * 4) * 32 + lane;
               const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
               const double* rowp = a.diagDM + diag_base(tp);
-              const double* rown = a.diagDM + diag_base(tn) + tn;
+              const double* rown = a.diagDM + diag_base(tn);  // indexed by tn - cn
 #pragma unroll
               for (int q = 0; q < 4; q++) {
                 const uint4 pvp = __ldg(P0 + q * 32), pvn = __ldg(P1 + q * 32);
@@ -630,8 +642,8 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
                   const uint32_t vp = s_base[0][i][tid] + prp[k] - s_cnt[0][M == 2 ? i : 0][tid];
                   const uint32_t vn = s_base[M - 1][i][tid] + prn[k] - s_cnt[M == 2 ? 1 : 0][M == 2 ? i : 0][tid];
                   // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
-                  const double vlo = __ldg(rowp + (vp & 0xffffu)) + __ldg(rown - (vn & 0xffffu));
-                  const double vhi = __ldg(rowp + (vp >> 16)) + __ldg(rown - (vn >> 16));
+                  const double vlo = lookup_f64(rowp, vp & 0xffffu) + lookup_f64(rown, tn - (vn & 0xffffu));
+                  const double vhi = lookup_f64(rowp, vp >> 16) + lookup_f64(rown, tn - (vn >> 16));
                   best[((i & 1) * 2) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2) * 8 + (i >> 1)], __double2float_rn(vlo));
                   best[((i & 1) * 2 + 1) * 8 + (i >> 1)] = fmaxf(best[((i & 1) * 2 + 1) * 8 + (i >> 1)], __double2float_rn(vhi));
                 }
@@ -644,19 +656,19 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
             for (int b = 0; b < 32; b++) {
               const uint32_t v = c16[GCRE_C16_REG(b)];
               const uint32_t c = GCRE_C16_HI(b) ? (v >> 16) : (v & 0xffffu);
-              best[b] = fmaxf(best[b], __ldg(row + c));
+              best[b] = fmaxf(best[b], lookup_f32(row, c));
             }
           } else {
             const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
             const double* rowp = a.diagDM + diag_base(tp);
-            const double* rown = a.diagDM + diag_base(tn) + tn;
+            const double* rown = a.diagDM + diag_base(tn);  // indexed by tn - cn
 #pragma unroll
             for (int b = 0; b < 32; b++) {
               const uint32_t vp = s_cnt[0][M == 2 ? GCRE_C16_REG(b) : 0][tid], vn = s_cnt[M == 2 ? 1 : 0][M == 2 ? GCRE_C16_REG(b) : 0][tid];
               const uint32_t cp = GCRE_C16_HI(b) ? (vp >> 16) : (vp & 0xffffu);
               const uint32_t cn = GCRE_C16_HI(b) ? (vn >> 16) : (vn & 0xffffu);
               // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
-              const double v = __ldg(rowp + cp) + __ldg(rown - cn);
+              const double v = lookup_f64(rowp, cp) + lookup_f64(rown, tn - cn);
               best[b] = fmaxf(best[b], __double2float_rn(v));
             }
           }

@@ -263,19 +263,19 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
           for (int q = 0; q < 2 * R; q++) {
             const uint32_t v = cnt[0][q >> 1];
             const uint32_t c = (q & 1) ? (v >> 16) : (v & 0xffffu);
-            best[q] = fmaxf(best[q], __ldg(row + c));
+            best[q] = fmaxf(best[q], lookup_f32(row, c));
           }
         } else {
           const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
           const double* rowp = a.diagDM + diag_base(tp);
-          const double* rown = a.diagDM + diag_base(tn) + tn;
+          const double* rown = a.diagDM + diag_base(tn);  // indexed by tn - cn
 #pragma unroll
           for (int q = 0; q < 2 * R; q++) {
             const uint32_t vp = cnt[0][q >> 1], vn = cnt[M - 1][q >> 1];
             const uint32_t cp = (q & 1) ? (vp >> 16) : (vp & 0xffffu);
             const uint32_t cn = (q & 1) ? (vn >> 16) : (vn & 0xffffu);
             // src/methods.h:223-227: vtmax[pcp][total_pos - pcp] + vtmax[total_neg - pnp][pnp]
-            const double v = __ldg(rowp + cp) + __ldg(rown - cn);
+            const double v = lookup_f64(rowp, cp) + lookup_f64(rown, tn - cn);
             best[q] = fmaxf(best[q], __double2float_rn(v));
           }
         }
