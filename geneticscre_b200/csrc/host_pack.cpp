@@ -5,9 +5,11 @@
 // over a 55 GB/s PCIe link (22 ms) - if the host cores can stream them faster than that, packing first and uploading the
 // 37 MB of bits wins, and it also takes pageable R memory (which the driver stages at a fraction of the link rate) off
 // the copy path.  The device-side pack kernel stays for small inputs and as the fallback (gcre_capi.cu picks).
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <thread>
 #include <vector>
 
@@ -69,16 +71,26 @@ void pack_i32_rows(const int32_t* data, size_t rows, int cols, uint64_t* out, si
     work(0, rows);
     return;
   }
+  // Rows are handed out in small chunks from a shared counter (the calling thread takes part): on a shared host a thread whose
+  // core is taken away for a few milliseconds then delays only its current chunk, not a sixteenth of the matrix - with a static
+  // split single end-to-end steps were stretched by tens of milliseconds.
+  const size_t chunk = std::max<size_t>(1, std::min<size_t>(64, rows / ((size_t)threads * 8)));
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      const size_t r0 = next.fetch_add(chunk, std::memory_order_relaxed);
+      if (r0 >= rows) return;
+      work(r0, std::min(rows, r0 + chunk));
+    }
+  };
   std::vector<std::thread> pool;
-  bool all_started = true;
   try {
-    pool.reserve(threads);
-    for (int t = 0; t < threads; t++) pool.emplace_back(work, rows * t / threads, rows * (t + 1) / threads);
-  } catch (...) {  // thread creation refused (resource limits): finish on the calling thread - the work is idempotent
-    all_started = false;
+    pool.reserve(threads - 1);
+    for (int t = 1; t < threads; t++) pool.emplace_back(worker);
+  } catch (...) {  // thread creation refused (resource limits): the threads that did start and this one finish the work
   }
+  worker();
   for (auto& th : pool) th.join();
-  if (!all_started) work(0, rows);
 }
 
 }  // namespace gcre_host
