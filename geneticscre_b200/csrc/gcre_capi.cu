@@ -310,7 +310,7 @@ static void unpool_event(int device, bool timing, cudaEvent_t ev) {
 struct gcre_pathset;
 struct gcre_uidset;
 
-constexpr unsigned kSpecCand = 1024;  // candidates copied to the host speculatively with the scalars (a 12 M-pair join appends ~300)
+constexpr unsigned kSpecCand = 8192;  // candidates copied to the host speculatively with the scalars (192 KB; the joins of the bench append 2,000 - 6,000)
 
 struct gcre_exec {
   int M = 1, n_cases = 0, n_ctrls = 0, n = 0, W64 = 0, Wp = 0, iters = 0, Ip = 0, Iw = 0, device = 0, sm_count = 0;
@@ -1290,16 +1290,19 @@ extern "C" int gcre_merge_topk(const gcre_score* lists, const int* list_sizes, i
 // ------------------------------------------------------------------------------------------------------------------
 // carrier-list views for the sparse kernels
 // ------------------------------------------------------------------------------------------------------------------
+constexpr unsigned long long kViewBoundEntries = 16ull << 20;  // carrier lists up to this many entries (32 / 64 MB) are allocated by their bound
 static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
   if (ps->view.valid) return GCRE_OK;
   CKS(materialize_zero(ps));
   {  // (re)build lists and stats; counts emitted with the rows stay - the rows have not changed
     uint32_t* pcnt = ps->view.pcnt;
     const unsigned long long gen = ps->view.pcnt_gen, elo = ps->view.emit_lo, ehi = ps->view.emit_hi;
+    const int layout = ps->view.pcnt_layout;
     ps->view.pcnt = nullptr;
     drop_view(ps);
     ps->view.pcnt = pcnt;
     ps->view.pcnt_gen = gen;
+    ps->view.pcnt_layout = layout;
     ps->view.emit_lo = elo;
     ps->view.emit_hi = ehi;
   }
@@ -1323,8 +1326,16 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
     CKS(ex->scan_tmp.ensure(tmp_bytes));
     CK(cub::DeviceScan::ExclusiveSum(ex->scan_tmp.p, tmp_bytes, padded, ps->view.off, (long long)(items + 1), ex->stream));
     LAUNCHED();
-    CK(cudaMemcpyAsync(&total, ps->view.off + items, 8, cudaMemcpyDeviceToHost, ex->stream));
-    CK(cudaStreamSynchronize(ex->stream));
+    // How many entries to allocate.  join_impl has the set's largest half-row by now (an upper bound is enough): when rows x
+    // that bound is small the lists are allocated by the bound and the host does not wait for the scan's total
+    // (one device round trip per view, ~10 views per level schedule).
+    const unsigned long long bound = ps->max_half_pop >= 0 ? (unsigned long long)items * (((unsigned long long)ps->max_half_pop + 7ull) & ~7ull) : ~0ull;
+    if (bound <= kViewBoundEntries && !std::getenv("GCRE_TEST_VIEW_EXACT")) {
+      total = bound;
+    } else {
+      CK(cudaMemcpyAsync(&total, ps->view.off + items, 8, cudaMemcpyDeviceToHost, ex->stream));
+      CK(cudaStreamSynchronize(ex->stream));
+    }
   }
   ps->view.total = (size_t)total;
   const bool wide = sparse_wide(ex->n);
@@ -1353,9 +1364,10 @@ static int ensure_view(gcre_exec* ex, gcre_pathset* ps) {
 
 // per-permutation counts of every (row, half) of a path set under the exec's current masks (join_sparse.cuh, PC kernels)
 static int ensure_precount(gcre_exec* ex, gcre_pathset* ps) {
-  if (ps->view.pcnt && ps->view.pcnt_gen == ex->mask_gen) return GCRE_OK;
+  if (ps->view.pcnt && ps->view.pcnt_gen == ex->mask_gen && ps->view.pcnt_layout == 0) return GCRE_OK;
   dev_free(ex, ps->view.pcnt);
   ps->view.pcnt = nullptr;
+  ps->view.pcnt_layout = 0;
   const long long items = (long long)ps->size * ex->M;
   const int nb = ex->Iw / 32;
   CK(dev_alloc(ex, (void**)&ps->view.pcnt, std::max<size_t>((size_t)items * nb, 1) * 2048));
@@ -1654,9 +1666,20 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   memset(&sp, 0, sizeof sp);
   if (kernel == GCRE_KERNEL_SPARSE) {
     CKS(ensure_patient_major(ex));
+    // <= 512 permutations: the split-carrier kernels (join_sparse_sc.cuh) run instead - unless pre-counted partners are forced
+    // (GCRE_PRECOUNT=1) - and emit / consume count tables in their own, smaller layout
+    size_t budget = (size_t)24 << 30;  // device bytes a table of per-permutation counts may take (GCRE_PRECOUNT_MAX_MB overrides)
+    if (const char* mb = std::getenv("GCRE_PRECOUNT_MAX_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
+    const int n_perm_blocks = ex->Iw / 32;
+    const bool few_perms = sparse_sc_enabled(ex->Ip, n_perm_blocks);
+    int pc_mode = precount_mode(pair_hi - pair_lo, paths1->size, ex->M, n_perm_blocks, budget);
+    if (few_perms && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;  // the split-carrier kernel is the better form there
+    const bool split = few_perms && pc_mode != PRECOUNT_YES;
+    const int layout = split ? sparse_sc_words(ex->Ip) : 0;
+    const size_t entry_bytes = split ? sparse_sc_table_bytes(ex->Ip) : (size_t)n_perm_blocks * 2048;  // per (row, half)
     // upstream operand: rows that came out of a KEEP join carry their counts and totals - no carrier lists needed
-    const bool base_emitted = paths0->view.pcnt && paths0->view.pcnt_gen == ex->mask_gen && paths0->view.stats_valid && paths0 != paths_res &&
-                              ub >= paths0->view.emit_lo && ue <= paths0->view.emit_hi;
+    const bool base_emitted = paths0->view.pcnt && paths0->view.pcnt_gen == ex->mask_gen && paths0->view.pcnt_layout == layout &&
+                              paths0->view.stats_valid && paths0 != paths_res && ub >= paths0->view.emit_lo && ue <= paths0->view.emit_hi;
     if (!base_emitted) CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths0)));
     CKS(ensure_view(ex, const_cast<gcre_pathset*>(paths1)));
     sp.off0 = paths0->view.off; sp.len0 = paths0->view.len; sp.car0 = paths0->view.car; sp.ncase0 = paths0->view.ncase;
@@ -1666,19 +1689,14 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     sp.unit_prefix = (const unsigned long long*)us->units.p;
     sp.unit_idx = (const uint32_t*)us->unit_idx.p;
     sp.work_counter = (unsigned long long*)(ex->d_scalars + 2);
-    sp.n_perm_blocks = ex->Iw / 32;
+    sp.n_perm_blocks = n_perm_blocks;
     sp.exact_pairs = reinterpret_cast<unsigned long long*>(ex->d_scalars + 4);
-    size_t budget = (size_t)24 << 30;  // device bytes a table of per-permutation counts may take (GCRE_PRECOUNT_MAX_MB overrides)
-    if (const char* mb = std::getenv("GCRE_PRECOUNT_MAX_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
-    // kept rows take their counts along (join_sparse.cuh) when result rows are the running sums of the counts (res_is_prefix:
-    // rows [pair_lo, pair_hi) are exactly the ones this call writes); GCRE_TEST_EMIT=0 (test hook) turns it off
+    // kept rows take their counts along (join_sparse.cuh, join_sparse_sc.cuh) when result rows are the running sums of the
+    // counts (res_is_prefix: rows [pair_lo, pair_hi) are exactly the ones this call writes); GCRE_TEST_EMIT=0 (test hook) turns it off
     const char* emit_env = std::getenv("GCRE_TEST_EMIT");
-    // <= 512 permutations: the split-carrier kernel (join_sparse_sc.cuh) runs instead and neither writes nor reads count tables
-    const bool few_perms = sparse_sc_enabled(ex->Ip, sp.n_perm_blocks);
-    const bool emit = !few_perms && keep && pair_hi > pair_lo && us->res_is_prefix && paths_res != paths0 && paths_res != paths1 && !(emit_env && *emit_env == '0') &&
-                      (size_t)paths_res->size * ex->M * sp.n_perm_blocks * 2048 <= budget;
-    int pc_mode = emit ? PRECOUNT_NO : precount_mode(pair_hi - pair_lo, paths1->size, ex->M, sp.n_perm_blocks, budget);
-    if (few_perms && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;  // the split-carrier kernel is the better form there
+    const bool emit = (split || !few_perms) && keep && pair_hi > pair_lo && us->res_is_prefix && paths_res != paths0 && paths_res != paths1 &&
+                      !(emit_env && *emit_env == '0') && (size_t)paths_res->size * ex->M * entry_bytes <= budget;
+    if (emit && !split) pc_mode = PRECOUNT_NO;  // the emitting form of the 1,024-permutation kernel has no pre-counted variant
     if (pc_mode == PRECOUNT_SAMPLE) {
       // how much of a partner row is already in its upstream row: 2,048 pairs spread over the join (~40 us incl. the read-back)
       JoinParams q;
@@ -1711,7 +1729,8 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     if (keep && paths_res != paths0 && paths_res != paths1) drop_view(paths_res);  // its rows are about to be rewritten
     if (emit) {
       const size_t items = (size_t)paths_res->size * ex->M;
-      CK(dev_alloc(ex, (void**)&paths_res->view.pcnt, items * sp.n_perm_blocks * 2048));
+      CK(dev_alloc(ex, (void**)&paths_res->view.pcnt, items * entry_bytes));
+      paths_res->view.pcnt_layout = layout;
       CK(dev_alloc(ex, (void**)&paths_res->view.len, items * 4));
       CK(dev_alloc(ex, (void**)&paths_res->view.ncase, items * 4));
       sp.pcnt_res = paths_res->view.pcnt;

@@ -78,6 +78,7 @@ struct SparseView {
   // [item][perm block][q = 0..3][lane][4] u32 = packed u16 pairs (registers 4q..4q+3 of GCRE_C16_REG) - 2 KB per block
   uint32_t* pcnt = nullptr;
   unsigned long long pcnt_gen = 0;  // exec->mask_gen the table was built for
+  int pcnt_layout = 0;              // 0: the image above; 4 / 8 / 16: the split-carrier kernels' (join_sparse_sc.cuh: [item][lane][NW / 2] u32)
   // rows whose counts / ranges / len / ncase were emitted: a KEEP join over a shard of its upstream rows (multi-GPU: each
   // rank builds only the rows its shard of the next level consumes) fills [emit_lo, emit_hi) only
   unsigned long long emit_lo = 0, emit_hi = 0;
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(128) build_precount_kernel(const unsigned long
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // CT = carrier index type of the list views: uint16_t (n <= 65,535) or uint32_t
 // THR: thresholded look-ups (below) instead of 32 running maxima per lane in registers

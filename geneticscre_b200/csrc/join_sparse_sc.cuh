@@ -12,8 +12,18 @@
 // the heavy-tailed list lengths; splitting one pair's carriers has no such imbalance.)
 //
 // Everything else - units, filter against the dense upstream row, true scores, candidates with the self-tightening
-// threshold, kept rows - is as in join_sparse.cuh.  No count tables are emitted or consumed here: the base of a unit is
-// walked the same split way and costs an eighth of what it does there.
+// threshold, kept rows - is as in join_sparse.cuh.
+//
+// Per-pair cost is what matters here (a pair brings ~15 new carriers of 4 words), so:
+//  * a half whose new carriers fit HALF a batch (<= 4 per sub-group: the common case) takes a short path - 1 or 4 gathers per
+//    lane, a 3-plane carry-save sum, BYTE counts and a 7-shuffle reduce-scatter over bytes instead of the 8-gather / 8-plane /
+//    16-register form (about 90 fewer warp instructions per half);
+//  * the true score of a pair (two 64-bit triangle offsets, f64 loads, candidate test) is parked in lane (j mod 32) and worked
+//    off by all lanes at once every 32 pairs instead of by lane 0 behind every pair;
+//  * the offsets / lengths of the next partner's lists are loaded one pair ahead;
+//  * KEEP joins emit the counts of the kept rows (R registers per lane and half: 256 B per row and half at <= 128
+//    permutations) with their carrier totals, and the next level takes them as the base of its units: it then needs neither
+//    the carrier lists of its upstream rows (two passes over the kept rows to build) nor the walk over them.
 #pragma once
 #include "join_sparse.cuh"
 
@@ -24,7 +34,10 @@ constexpr int THREADS = 128;
 constexpr int WARPS = THREADS / 32;
 constexpr int QCAP = 128;       // the batch being drained (<= 64 slots) + the < 32 entries that can wait behind it, in whole batches
 constexpr int MAX_PERMS = 512;  // 16 words of 32
-constexpr int min_blocks(int nw) { return nw == 16 ? 6 : 8; }
+#ifndef GCRE_SC_MB4
+#define GCRE_SC_MB4 8  // resident CTAs per SM the <= 128-permutation kernels are compiled for (64 registers)
+#endif
+constexpr int min_blocks(int nw) { return nw == 16 ? 6 : nw == 8 ? 8 : GCRE_SC_MB4; }
 }  // namespace sparse_sc
 
 // position of the t-th queued carrier: inside its batch of B = 8 G the entries of sub-group s = t % G are contiguous (two
@@ -69,17 +82,74 @@ __device__ __forceinline__ void sc_reduce_scatter(const uint32_t (&c16)[16], int
   }
 }
 
+// the same over BYTE counts (every sum <= 255): r8[s] holds the four counts of bits s, s+8, s+16, s+24 -> the NW / 4
+// registers NW/4 * sub .. of the lane's sub-group, 7 / 6 / 4 shuffles
+template <int NW>
+__device__ __forceinline__ void sc_reduce_scatter_bytes(const uint32_t (&r8)[8], int lane, uint32_t (&ob)[NW / 4]) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+  uint32_t r4[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t send = b4 ? r8[k] : r8[k + 4], keep = b4 ? r8[k + 4] : r8[k];
+    r4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  if constexpr (NW == 16) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) ob[k] = r4[k];
+  } else {
+    uint32_t r2[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const uint32_t send = b3 ? r4[k] : r4[k + 2], keep = b3 ? r4[k + 2] : r4[k];
+      r2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    if constexpr (NW == 8) {
+      ob[0] = r2[0];
+      ob[1] = r2[1];
+    } else {
+      const uint32_t send = b2 ? r2[0] : r2[1], keep = b2 ? r2[1] : r2[0];
+      ob[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+}
+
+// R packed-u16 registers of one lane and half in a count table (emitted by a KEEP join, base of the next level's units)
+template <int R>
+__device__ __forceinline__ void sc_table_load(const uint32_t* p, uint32_t (&v)[R]) {
+  if constexpr (R == 2) {
+    const uint2 t = __ldcs(reinterpret_cast<const uint2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < R; k += 4) {
+      const uint4 t = __ldcs(reinterpret_cast<const uint4*>(p + k));
+      v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+    }
+  }
+}
+template <int R>
+__device__ __forceinline__ void sc_table_store(uint32_t* p, const uint32_t (&v)[R]) {
+  if constexpr (R == 2) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(v[0], v[1]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < R; k += 4) __stcs(reinterpret_cast<uint4*>(p + k), make_uint4(v[k], v[k + 1], v[k + 2], v[k + 3]));
+  }
+}
+
 template <int M, bool KEEP, typename CT, int NW>
 __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW)) join_sparse_sc_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse_sc;
   constexpr int PB = sparse::PB, FLUSH_AT = sparse::FLUSH_AT;
   constexpr int G = 32 / NW;          // sub-groups sharing one pair's carriers
   constexpr uint32_t B = 8 * G;       // carriers per batch
+  constexpr uint32_t SHORT = B / 2;   // new carriers of a half the short path takes (<= 4 per sub-group)
   constexpr int R = NW / 2;           // packed count registers (2 permutations each) a lane keeps after the reduce-scatter
   constexpr int NCOPY = (B == 64) ? 2 : 1;  // 32-slot pieces that can hold the < 32 entries left behind a drained batch
   const CT* car0 = static_cast<const CT*>(s.car0);
   const CT* car1 = static_cast<const CT*>(s.car1);
   __shared__ __align__(16) uint32_t s_queue[WARPS][QCAP];
+  __shared__ __align__(16) uint32_t s_park[WARPS][32][2 * M];  // totals of the last <= 32 pairs of the warp's unit
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int w = lane % NW, sub = lane / NW;
@@ -108,12 +178,9 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
     const uint64_t* p0row = a.p0 + (size_t)idx * row_words;
     const uint32_t loc0 = a.location[idx];
 
-    uint32_t pl[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) pl[j] = 0;
-    int inbatch = 0, inreal = 0;
-
-    auto acc8 = [&](uint32_t (&c16)[16], const uint32_t (&x)[8], int real, bool last) {
+    // eight words into the bit planes of a walk; flushed into the packed counters when nearly full and behind the last batch
+    // (planes and batch counters belong to one walk and are zero again after its last flush)
+    auto acc8 = [&](uint32_t (&c16)[16], uint32_t (&pl)[8], int& inbatch, int& inreal, const uint32_t (&x)[8], int real, bool last) {
       hs8(pl, x);
       inbatch += 8;
       inreal += real;
@@ -123,56 +190,93 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
       }
     };
 
-    // ---- base: the upstream row's own carriers, 64 per step, sub-group `sub` takes the sub-th group of eight ----
+    // ---- base: counts of the upstream row's own carriers for this lane's permutations ----
     uint32_t t0[M], nc0[M], base[M][R];
+    if (s.pcnt0) {  // emitted by the join that made the upstream rows
 #pragma unroll
-    for (int h = 0; h < M; h++) {
-      t0[h] = nc0[h] = 0;
+      for (int h = 0; h < M; h++) {
+        const size_t item = (size_t)idx * M + h;
+        t0[h] = s.len0[item];
+        nc0[h] = s.ncase0[item];
+        sc_table_load<R>(s.pcnt0 + (item * 32 + lane) * R, base[h]);
+      }
+    } else {  // walk the row's carrier list, 8 G per step, sub-group `sub` takes the sub-th group of eight
 #pragma unroll
-      for (int k = 0; k < R; k++) base[h][k] = 0;
-    }
+      for (int h = 0; h < M; h++) {
+        t0[h] = nc0[h] = 0;
+#pragma unroll
+        for (int k = 0; k < R; k++) base[h][k] = 0;
+      }
 #pragma unroll 1
-    for (int h = 0; h < M; h++) {
-      uint32_t acc[16];
+      for (int h = 0; h < M; h++) {
+        uint32_t acc[16], pl[8];
 #pragma unroll
-      for (int i = 0; i < 16; i++) acc[i] = 0;
-      const size_t item = (size_t)idx * M + h;
-      const CT* lst0 = car0 + s.off0[item];
-      const uint32_t plen = (uint32_t)(s.off0[item + 1] - s.off0[item]);
-      const uint32_t t0h = s.len0[item], nc0h = s.ncase0[item];
+        for (int i = 0; i < 16; i++) acc[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) pl[i] = 0;
+        int inbatch = 0, inreal = 0;
+        const size_t item = (size_t)idx * M + h;
+        const CT* lst0 = car0 + s.off0[item];
+        const uint32_t plen = (uint32_t)(s.off0[item + 1] - s.off0[item]);
+        const uint32_t t0h = s.len0[item], nc0h = s.ncase0[item];
 #pragma unroll 1
-      for (uint32_t i = 0; i < plen; i += B) {
-        uint32_t x[8];
-        if (i + sub * 8 < plen) {
-          uint32_t c[8];
-          load8(lst0 + i + sub * 8, c);
+        for (uint32_t i = 0; i < plen; i += B) {
+          uint32_t x[8];
+          if (i + sub * 8 < plen) {
+            uint32_t c[8];
+            load8(lst0 + i + sub * 8, c);
 #pragma unroll
-          for (int q = 0; q < 8; q++) x[q] = __ldg(word_ptr(pt_lane, c[q] * (uint32_t)Iw));
-        } else {
+            for (int q = 0; q < 8; q++) x[q] = __ldg(word_ptr(pt_lane, c[q] * (uint32_t)Iw));
+          } else {
 #pragma unroll
-          for (int q = 0; q < 8; q++) x[q] = 0u;
+            for (int q = 0; q < 8; q++) x[q] = 0u;
+          }
+          acc8(acc, pl, inbatch, inreal, x, 8, i + B >= plen);
         }
-        acc8(acc, x, 8, i + B >= plen);
-      }
-      uint32_t rr[R];
-      sc_reduce_scatter<NW>(acc, lane, rr);
-      if (M == 1 || h == 0) {
-        t0[0] = t0h; nc0[0] = nc0h;
+        uint32_t rr[R];
+        sc_reduce_scatter<NW>(acc, lane, rr);
+        if (M == 1 || h == 0) {
+          t0[0] = t0h; nc0[0] = nc0h;
 #pragma unroll
-        for (int k = 0; k < R; k++) base[0][k] = rr[k];
-      } else {
-        t0[M - 1] = t0h; nc0[M - 1] = nc0h;
+          for (int k = 0; k < R; k++) base[0][k] = rr[k];
+        } else {
+          t0[M - 1] = t0h; nc0[M - 1] = nc0h;
 #pragma unroll
-        for (int k = 0; k < R; k++) base[M - 1][k] = rr[k];
+          for (int k = 0; k < R; k++) base[M - 1][k] = rr[k];
+        }
       }
     }
+
+    // list offsets / lengths of a partner's halves (in the order they are joined into the upstream halves): loaded one pair ahead
+    bool flip_n = true;
+    unsigned long long off_n[M];
+    uint32_t len_n[M];
+    auto load_meta = [&](uint32_t loc) {
+      if (M == 2) flip_n = need_flip(a.path_length, a.signs, idx, loc);
+#pragma unroll
+      for (int h = 0; h < M; h++) {
+        const int hh = (M == 1) ? 0 : (flip_n ? h : 1 - h);
+        const size_t item = (size_t)loc * M + hh;
+        off_n[h] = s.off1[item];
+        len_n[h] = s.len1[item];
+      }
+    };
+    load_meta(loc0 + j0);
 
     bool base_done = false;
     // ---- partners ----
     for (uint32_t j = j0; j < j1; j++) {
       const uint32_t loc = loc0 + j;
-      bool flip = true;
-      if (M == 2) flip = need_flip(a.path_length, a.signs, idx, loc);
+      const uint32_t park = (j - j0) & 31u;  // slot of this pair in s_park
+      const bool flip = flip_n;
+      unsigned long long off[M];
+      uint32_t lenh[M];
+#pragma unroll
+      for (int h = 0; h < M; h++) {
+        off[h] = off_n[h];
+        lenh[h] = len_n[h];
+      }
+      load_meta(loc0 + min(j + 1, j1 - 1));
       uint32_t nd[M], ncn[M], cnt[M][R];
 #pragma unroll
       for (int h = 0; h < M; h++) {
@@ -182,14 +286,15 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
       }
 #pragma unroll 1
       for (int h = 0; h < M; h++) {
-        uint32_t c16[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) c16[i] = 0;
-        const int hh = (M == 1) ? 0 : (flip ? h : 1 - h);
-        const size_t item = (size_t)loc * M + hh;
-        const CT* lst1 = car1 + s.off1[item];
-        const uint32_t len = s.len1[item];
+        const CT* lst1 = car1 + ((M == 1 || h == 0) ? off[0] : off[M - 1]);
+        const uint32_t len = (M == 1 || h == 0) ? lenh[0] : lenh[M - 1];
         const uint64_t* p0h = p0row + h * Wp;
+        uint32_t c16[16], pl[8];  // general path only: zeroed by its first drain
+        int inbatch = 0, inreal = 0;
+        uint32_t rr[R];    // counts of the half's new carriers for this lane's permutations
+#pragma unroll
+        for (int k = 0; k < R; k++) rr[k] = 0;
+        bool counted = len == 0;
         uint32_t ndh = 0, ncnh = 0;
         uint32_t qn = 0;
 #pragma unroll 1
@@ -204,10 +309,55 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
           if (keep) queue[sc_slot<G>(qn + __popc(km & lt_mask))] = c * (uint32_t)Iw;
           qn += __popc(km);
           const bool last_chunk = i0 + 32 >= len;
+          if (last_chunk && ndh == 0 && qn <= SHORT) {
+            // ---- short path: everything new fits half a batch; entry t sits at position t / G (< 4) of sub-group t % G ----
+            if (qn > 0) {
+              if ((uint32_t)lane >= qn && (uint32_t)lane < SHORT) queue[sc_slot<G>((uint32_t)lane)] = zero_row;
+              __syncwarp();
+              const uint4 lo = *reinterpret_cast<const uint4*>(queue + sub * 8);
+              __syncwarp();
+              uint32_t r8[8];  // byte counts: byte q of r8[t] <-> bit q*8 + t of the lane's word
+              if (qn <= (uint32_t)G) {  // at most one carrier per sub-group
+                const uint32_t x0 = __ldg(word_ptr(pt_lane, lo.x));
+#pragma unroll
+                for (int t = 0; t < 8; t++) r8[t] = (x0 >> t) & 0x01010101u;
+              } else {
+                const uint32_t x0 = __ldg(word_ptr(pt_lane, lo.x)), x1 = __ldg(word_ptr(pt_lane, lo.y));
+                const uint32_t x2 = __ldg(word_ptr(pt_lane, lo.z)), x3 = __ldg(word_ptr(pt_lane, lo.w));
+                uint32_t c1, s1;
+                csa(c1, s1, x0, x1, x2);
+                const uint32_t q0 = s1 ^ x3, c2 = s1 & x3;
+                const uint32_t q1 = c1 ^ c2, q2 = c1 & c2;
+#pragma unroll
+                for (int t = 0; t < 8; t++) r8[t] = ((q0 >> t) & 0x01010101u) | ((t >= 1 ? (q1 >> (t - 1)) : (q1 << 1)) & 0x02020202u);
+                if (qn > 3u * G) {  // some sub-group holds four
+#pragma unroll
+                  for (int t = 0; t < 8; t++) r8[t] |= (t >= 2 ? (q2 >> (t - 2)) : (q2 << (2 - t))) & 0x04040404u;
+                }
+              }
+              uint32_t ob[NW / 4];
+              sc_reduce_scatter_bytes<NW>(r8, lane, ob);
+#pragma unroll
+              for (int k = 0; k < NW / 4; k++) {
+                rr[2 * k] = __byte_perm(ob[k], 0u, 0x4140);
+                rr[2 * k + 1] = __byte_perm(ob[k], 0u, 0x4342);
+              }
+              ndh = qn;
+              qn = 0;
+            }
+            counted = true;
+            break;
+          }
           // drain whole batches of B; after the last chunk also the remainder (padded with the zero row), and at least once
           // when counts of an earlier batch are still in the planes
 #pragma unroll 1
           while (qn >= B || (last_chunk && (qn > 0 || inbatch > 0))) {
+            if (ndh == 0) {
+#pragma unroll
+              for (int t = 0; t < 16; t++) c16[t] = 0;
+#pragma unroll
+              for (int t = 0; t < 8; t++) pl[t] = 0;
+            }
             const uint32_t real = min(qn, B);
             if (real < B) {
               for (uint32_t t = real + lane; t < B; t += 32) queue[sc_slot<G>(t)] = zero_row;
@@ -224,7 +374,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
             x[6] = __ldg(word_ptr(pt_lane, hi.z));
             x[7] = __ldg(word_ptr(pt_lane, hi.w));
             const uint32_t rem = qn - real;                      // < 32 entries waiting behind the drained batch
-            acc8(c16, x, (int)((real + G - 1) / G), last_chunk && rem == 0);
+            acc8(c16, pl, inbatch, inreal, x, (int)((real + G - 1) / G), last_chunk && rem == 0);
             // they move to the front: the slot layout is per batch, so whole batches are copied as they are
             uint32_t mv[NCOPY];
 #pragma unroll
@@ -239,8 +389,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
             qn = rem;
           }
         }
-        uint32_t rr[R];
-        sc_reduce_scatter<NW>(c16, lane, rr);
+        if (!counted) sc_reduce_scatter<NW>(c16, lane, rr);
         if (M == 1 || h == 0) {
           nd[0] = ndh; ncn[0] = ncnh;
 #pragma unroll
@@ -281,11 +430,23 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
         }
       }
 
-      // ---- kept joined row (src/join_base.cpp:246-249) ----
       if (KEEP) {
+        const size_t r = (size_t)(a.res_idx[idx] + j);
+        // ---- the kept row's counts and carrier totals travel with it (base of the next level's units) ----
+        if (s.pcnt_res) {
+#pragma unroll
+          for (int h = 0; h < M; h++) {
+            sc_table_store<R>(s.pcnt_res + ((r * M + h) * 32 + lane) * R, cnt[h]);
+            if (lane == 0) {
+              s.len_res[r * M + h] = t0[h] + nd[h];
+              s.ncase_res[r * M + h] = nc0[h] + ncn[h];
+            }
+          }
+        }
+        // ---- kept joined row (src/join_base.cpp:246-249) ----
         const ulonglong2* u = reinterpret_cast<const ulonglong2*>(p0row);
         const ulonglong2* v = reinterpret_cast<const ulonglong2*>(a.p1 + (size_t)loc * row_words);
-        ulonglong2* out = reinterpret_cast<ulonglong2*>(a.pres + (size_t)(a.res_idx[idx] + j) * row_words);
+        ulonglong2* out = reinterpret_cast<ulonglong2*>(a.pres + r * row_words);
         const int Wv = Wp >> 1;
         const int vpos = (M == 2 && !flip) ? Wv : 0, vneg = (M == 2 && !flip) ? 0 : Wv;
 #pragma unroll 4
@@ -298,38 +459,60 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
           }
         }
       }
-      // ---- true score -> top-K candidate (src/methods.h:90-94, 253-264) ----
-      if (lane == 0) {
-        double score;
-        int cases, ctrls;
-        unsigned tmax;
+
+      // ---- true score -> top-K candidate (src/methods.h:90-94, 253-264): parked in lane (j - j0) mod 32, worked off by all
+      //      lanes at once every 32 pairs and behind the unit's last pair ----
+      if (lane == 0) {  // method 1: (carriers, case carriers); method 2: (tp, case_pos, tn, ctrl_pos)
+        if (M == 1) *reinterpret_cast<uint2*>(s_park[warp][park]) = make_uint2(t0[0] + nd[0], nc0[0] + ncn[0]);
+        else *reinterpret_cast<uint4*>(s_park[warp][park]) = make_uint4(t0[0] + nd[0], nc0[0] + ncn[0], t0[M - 1] + nd[M - 1], nc0[M - 1] + ncn[M - 1]);
+      }
+      if (park == 31u || j + 1 == j1) {
+        __syncwarp();
+        const bool mine = (uint32_t)lane <= park;
+        uint32_t pk[2 * M];
         if (M == 1) {
-          cases = (int)(nc0[0] + ncn[0]);
-          tmax = t0[0] + nd[0];
-          ctrls = (int)tmax - cases;
-          score = a.diagD[diag_base(tmax) + cases];
+          const uint2 t = *reinterpret_cast<const uint2*>(s_park[warp][lane]);
+          pk[0] = t.x; pk[1] = t.y;
         } else {
-          const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
-          const unsigned case_pos = nc0[0] + ncn[0], ctrl_neg = tp - case_pos;
-          const unsigned ctrl_pos = nc0[M - 1] + ncn[M - 1], case_neg = tn - ctrl_pos;
-          score = a.diagD[diag_base(tp) + case_pos] + a.diagD[diag_base(tn) + case_neg];
-          cases = (int)(case_pos + case_neg);
-          ctrls = (int)(ctrl_pos + ctrl_neg);
-          tmax = max(tp, tn);
+          const uint4 t = *reinterpret_cast<const uint4*>(s_park[warp][lane]);
+          pk[0] = t.x; pk[1] = t.y; pk[2 * M - 2] = t.z; pk[2 * M - 1] = t.w;
         }
-        if (KEEP) atomicMax(a.max_total, tmax);
-        if (score == score) {
+        const uint32_t locm = loc - park + (uint32_t)lane;
+        double score = 0.0;
+        int cases = 0, ctrls = 0;
+        unsigned tmax = 0;
+        if (mine) {
+          if (M == 1) {
+            cases = (int)pk[1];
+            tmax = pk[0];
+            ctrls = (int)tmax - cases;
+            score = a.diagD[diag_base(tmax) + cases];
+          } else {
+            const unsigned tp = pk[0], tn = pk[2 * M - 2];
+            const unsigned case_pos = pk[1], ctrl_neg = tp - case_pos;
+            const unsigned ctrl_pos = pk[2 * M - 1], case_neg = tn - ctrl_pos;
+            score = a.diagD[diag_base(tp) + case_pos] + a.diagD[diag_base(tn) + case_neg];
+            cases = (int)(case_pos + case_neg);
+            ctrls = (int)(ctrl_pos + ctrl_neg);
+            tmax = max(tp, tn);
+          }
+        }
+        if (KEEP) {
+          const unsigned m = __reduce_max_sync(0xffffffffu, tmax);
+          if (lane == 0) atomicMax(a.max_total, m);
+        }
+        if (mine && score == score) {
           const unsigned long long key = score_key(score);
           const unsigned long long dyn = a.n_slots ? __ldcg(a.dyn_thr) : 0ull;
           if (key > a.thr_key && key >= dyn) {
             const unsigned slot = atomicAdd(a.cand_count, 1u);
             if (slot < a.cand_cap) {
               Cand cd;
-              cd.key = key; cd.idx = idx; cd.loc = loc; cd.cases = cases; cd.ctrls = ctrls;
+              cd.key = key; cd.idx = idx; cd.loc = locm; cd.cases = cases; cd.ctrls = ctrls;
               a.cand[slot] = cd;
             }
             if (a.n_slots) {
-              const unsigned bucket = ((idx * 0x9E3779B1u) ^ (loc * 0x85EBCA6Bu)) >> 8;
+              const unsigned bucket = ((idx * 0x9E3779B1u) ^ (locm * 0x85EBCA6Bu)) >> 8;
               if (atomicMax(a.slots + bucket % (unsigned)a.n_slots, key) < key) {
                 unsigned long long m = ~0ull;
                 for (int t = 0; t < a.n_slots; t++) m = min(m, __ldcg(a.slots + t));
@@ -338,6 +521,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
             }
           }
         }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -351,12 +535,17 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
   }
 }
 
-// few permutations, no count tables in play; GCRE_TEST_NO_SPLIT=1 (test hook) keeps the one-word-per-lane kernel
+// few permutations, no pre-counted partners; GCRE_TEST_NO_SPLIT=1 (test hook) keeps the one-word-per-lane kernel
 static inline bool sparse_sc_enabled(int Ip, int n_perm_blocks) {
   return Ip <= sparse_sc::MAX_PERMS && n_perm_blocks == 1 && std::getenv("GCRE_TEST_NO_SPLIT") == nullptr;
 }
+// words per lane group (4, 8, 16): also the tag of the count-table layout these kernels emit and consume
+static inline int sparse_sc_words(int Ip) { return Ip <= 128 ? 4 : Ip <= 256 ? 8 : 16; }
+// bytes of one (row, half) entry of that table: 32 lanes x NW / 2 registers
+static inline size_t sparse_sc_table_bytes(int Ip) { return (size_t)32 * (sparse_sc_words(Ip) / 2) * 4; }
+// pcnt0 / pcnt_res, when set, must be in THIS layout (gcre_capi.cu tags every table with the layout it was emitted in)
 static inline bool sparse_sc_applies(const JoinParams& jp, const SparseParams& sp) {
-  return sparse_sc_enabled(jp.Ip, sp.n_perm_blocks) && !sp.pcnt0 && !sp.pcnt1 && !sp.pcnt_res;
+  return sparse_sc_enabled(jp.Ip, sp.n_perm_blocks) && !sp.pcnt1;
 }
 
 template <int M, bool KEEP, int NW>
@@ -369,8 +558,9 @@ static inline void launch_sparse_sc_ct(cudaStream_t stream, const JoinParams& jp
 
 template <int M, bool KEEP>
 static inline void launch_sparse_sc_nw(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int sm_count) {
-  if (jp.Ip <= 128) launch_sparse_sc_ct<M, KEEP, 4>(stream, jp, sp, sm_count);
-  else if (jp.Ip <= 256) launch_sparse_sc_ct<M, KEEP, 8>(stream, jp, sp, sm_count);
+  const int nw = sparse_sc_words(jp.Ip);
+  if (nw == 4) launch_sparse_sc_ct<M, KEEP, 4>(stream, jp, sp, sm_count);
+  else if (nw == 8) launch_sparse_sc_ct<M, KEEP, 8>(stream, jp, sp, sm_count);
   else launch_sparse_sc_ct<M, KEEP, 16>(stream, jp, sp, sm_count);
 }
 
