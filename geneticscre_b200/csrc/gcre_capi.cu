@@ -331,6 +331,10 @@ struct gcre_exec {
   uint64_t* d_pm = nullptr;     // word-major [Wp][Ip]
   uint32_t* d_pt = nullptr;     // patient-major [n][Iw], built on first use by a sparse kernel
   bool pt_valid = false;
+  // the same matrix with rows of exactly 4 / 8 / 16 words for the split-carrier kernels (<= 512 permutations): at 128-byte rows
+  // of which 16 bytes are used the matrix takes eight times the cache it needs (1.28 MB instead of 160 KB at 10,000 patients)
+  uint32_t* d_pt_sc = nullptr;
+  bool pt_sc_valid = false;
   unsigned long long mask_gen = 1;  // bumped whenever the permutation masks change: per-path-set pre-count tables depend on them
   // value table
   double* d_vt = nullptr;
@@ -544,7 +548,7 @@ extern "C" int gcre_exec_destroy(gcre_exec* ex) {
     ex->pathsets.clear();
     ex->uidsets.clear();
   }
-  for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
+  for (void* p : {(void*)ex->d_masks, (void*)ex->d_pm, (void*)ex->d_pt, (void*)ex->d_pt_sc, (void*)ex->d_vt, (void*)ex->d_diagD, (void*)ex->d_diagF,
                   (void*)ex->d_diagDM, (void*)ex->d_diagFM, (void*)ex->d_perm_max, (void*)ex->d_scalars, (void*)ex->d_topk})
     dev_free(ex, p);
   ex->cand.release();
@@ -794,7 +798,7 @@ static int rebuild_mask_layouts(gcre_exec* ex) {
     CK(cudaGetLastError());
       LAUNCHED();
   }
-  ex->pt_valid = false;
+  ex->pt_valid = ex->pt_sc_valid = false;
   ex->mask_gen++;
   return GCRE_OK;
 }
@@ -809,6 +813,19 @@ static int ensure_patient_major(gcre_exec* ex) {
   CK(cudaGetLastError());
       LAUNCHED();
   ex->pt_valid = true;
+  return GCRE_OK;
+}
+
+static int ensure_patient_major_sc(gcre_exec* ex) {
+  if (ex->pt_sc_valid) return GCRE_OK;
+  const int iw = sparse_sc_words(ex->Ip);
+  if (!ex->d_pt_sc) CK(dev_alloc(ex, (void**)&ex->d_pt_sc, (size_t)(ex->n + 1) * iw * 4));
+  CK(cudaMemsetAsync(ex->d_pt_sc + (size_t)ex->n * iw, 0, (size_t)iw * 4, ex->stream));
+  const long long warps = (long long)iw * ((ex->n + 31) / 32);
+  masks_to_patient_major_kernel<<<grid_for(warps * 32, 256), 256, 0, ex->stream>>>(ex->d_masks, ex->iters, ex->W64, ex->n, ex->d_pt_sc, iw);
+  CK(cudaGetLastError());
+  LAUNCHED();
+  ex->pt_sc_valid = true;
   return GCRE_OK;
 }
 
@@ -1665,7 +1682,6 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   SparseParams sp;
   memset(&sp, 0, sizeof sp);
   if (kernel == GCRE_KERNEL_SPARSE) {
-    CKS(ensure_patient_major(ex));
     // <= 512 permutations: the split-carrier kernels (join_sparse_sc.cuh) run instead - unless pre-counted partners are forced
     // (GCRE_PRECOUNT=1) - and emit / consume count tables in their own, smaller layout
     size_t budget = (size_t)24 << 30;  // device bytes a table of per-permutation counts may take (GCRE_PRECOUNT_MAX_MB overrides)
@@ -1676,6 +1692,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     if (few_perms && pc_mode == PRECOUNT_SAMPLE) pc_mode = PRECOUNT_NO;  // the split-carrier kernel is the better form there
     const bool split = few_perms && pc_mode != PRECOUNT_YES;
     const int layout = split ? sparse_sc_words(ex->Ip) : 0;
+    CKS(split ? ensure_patient_major_sc(ex) : ensure_patient_major(ex));
     const size_t entry_bytes = split ? sparse_sc_table_bytes(ex->Ip) : (size_t)n_perm_blocks * 2048;  // per (row, half)
     // upstream operand: rows that came out of a KEEP join carry their counts and totals - no carrier lists needed
     const bool base_emitted = paths0->view.pcnt && paths0->view.pcnt_gen == ex->mask_gen && paths0->view.pcnt_layout == layout &&
@@ -1758,9 +1775,10 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   jp.signs = (const int32_t*)us->signs.p;
   jp.path_length = path_length;
   jp.pm = ex->d_pm;
-  jp.pt = ex->d_pt;
+  const bool split_form = kernel == GCRE_KERNEL_SPARSE && sparse_sc_enabled(ex->Ip, sp.n_perm_blocks) && !sp.pcnt1;  // == sparse_sc_applies
+  jp.pt = split_form ? ex->d_pt_sc : ex->d_pt;
   jp.Ip = ex->Ip;
-  jp.Iw = ex->Iw;
+  jp.Iw = split_form ? sparse_sc_words(ex->Ip) : ex->Iw;
   jp.n_perm_tiles = ex->Ip / dense::TI;
   jp.diagD = ex->d_diagD;
   jp.diagF = ex->d_diagF;
@@ -1817,6 +1835,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
   int launches = 0;
   bool thresholded = false;
   unsigned long long exact_pairs = 0;
+  bool shared_masks = false;
   for (size_t si = 0; si < plan.size(); si++) {
     const Seg seg = plan[si];
     const unsigned long long p = seg.b, pe = seg.e;
@@ -1832,7 +1851,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
       sp.n_units = pe - p;
       CK(cudaMemsetAsync(ex->d_scalars + 2, 0, 6 * sizeof(unsigned), ex->stream));
       const bool thr = sparse_thr(ex->M, pair_hi - pair_lo);
-      if (sparse_sc_applies(jp, sp)) CK(launch_join_sparse_sc(ex->stream, jp, sp, ex->M, keep, ex->sm_count));
+      if (sparse_sc_applies(jp, sp)) CK(launch_join_sparse_sc(ex->stream, jp, sp, ex->M, keep, ex->sm_count, &shared_masks));
       else CK(launch_join_sparse(ex->stream, jp, sp, ex->M, keep, ex->sm_count, thr));
       thresholded = thresholded || (thr && !sparse_sc_applies(jp, sp));
       LAUNCHED();
@@ -1934,6 +1953,7 @@ static int join_impl(gcre_exec* ex, const gcre_uidset* us, const gcre_pathset* p
     opts->launches = launches;
     opts->precounted = sp.pcnt1 != nullptr;
     opts->split_carrier = kernel == GCRE_KERNEL_SPARSE && sparse_sc_applies(jp, sp);
+    opts->shared_masks = shared_masks;
     opts->thresholded = thresholded ? 1 : 0;
     opts->exact_pairs = exact_pairs;
   }

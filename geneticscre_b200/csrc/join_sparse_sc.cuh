@@ -32,6 +32,11 @@ namespace gcre {
 namespace sparse_sc {
 constexpr int THREADS = 128;
 constexpr int WARPS = THREADS / 32;
+// PTS form (<= 128 permutations, small cohorts): ONE CTA of 32 warps per SM with the whole patient-major mask matrix
+// ((n + 1) x 16 B) staged in its shared memory by a bulk async copy - the gathers of the hot loop become LDS, and L1 is left
+// to the carrier lists, the upstream rows and the score tables (with the matrix in L1 only a third of the gathers hit).
+constexpr int PTS_THREADS = 1024;
+constexpr size_t PTS_SMEM_MAX = 232448;  // 227 KB opt-in limit of a CTA on sm_100
 constexpr int QCAP = 128;       // the batch being drained (<= 64 slots) + the < 32 entries that can wait behind it, in whole batches
 constexpr int MAX_PERMS = 512;  // 16 words of 32
 #ifndef GCRE_SC_MB4
@@ -137,9 +142,17 @@ __device__ __forceinline__ void sc_table_store(uint32_t* p, const uint32_t (&v)[
   }
 }
 
-template <int M, bool KEEP, typename CT, int NW>
-__global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW)) join_sparse_sc_kernel(const JoinParams a, const SparseParams s) {
+// one 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar_smem) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar_smem)
+               : "memory");
+}
+
+template <int M, bool KEEP, typename CT, int NW, bool PTS>
+__global__ void __launch_bounds__(PTS ? sparse_sc::PTS_THREADS : sparse_sc::THREADS, PTS ? 1 : sparse_sc::min_blocks(NW))
+    join_sparse_sc_kernel(const JoinParams a, const SparseParams s) {
   using namespace sparse_sc;
+  constexpr int WARPS = (PTS ? PTS_THREADS : THREADS) / 32;
   constexpr int PB = sparse::PB, FLUSH_AT = sparse::FLUSH_AT;
   constexpr int G = 32 / NW;          // sub-groups sharing one pair's carriers
   constexpr uint32_t B = 8 * G;       // carriers per batch
@@ -159,6 +172,32 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
   uint32_t* queue = s_queue[warp];
   const uint32_t* pt_lane = a.pt + w;
   const uint32_t zero_row = (uint32_t)s.n * (uint32_t)Iw;
+  extern __shared__ __align__(128) uint32_t s_pt[];  // PTS: [(n + 1) * Iw] copy of a.pt
+  if constexpr (PTS) {
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    const uint32_t total = ((uint32_t)s.n + 1u) * (uint32_t)Iw * 4u;  // multiple of 16: Iw == 4
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_pt);
+      constexpr uint32_t PIECE = 32768;
+      for (uint32_t o = 0; o < total; o += PIECE) bulk_copy_g2s(dst + o, reinterpret_cast<const char*>(a.pt) + o, min(PIECE, total - o), bar);
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+    }
+  }
+  // word w of mask row `off` (a word offset c * Iw): shared memory (PTS) or the read-only path
+  auto pt_word = [&](uint32_t off) -> uint32_t {
+    if constexpr (PTS) return s_pt[off + (uint32_t)w];
+    else return __ldg(word_ptr(pt_lane, off));
+  };
 
   // permutations of this lane: (register i = R*sub + k, half hf)  <->  bit ((i & 1)*2 + hf)*8 + (i >> 1) of word w
   float best[2 * R];
@@ -226,7 +265,7 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
             uint32_t c[8];
             load8(lst0 + i + sub * 8, c);
 #pragma unroll
-            for (int q = 0; q < 8; q++) x[q] = __ldg(word_ptr(pt_lane, c[q] * (uint32_t)Iw));
+            for (int q = 0; q < 8; q++) x[q] = pt_word(c[q] * (uint32_t)Iw);
           } else {
 #pragma unroll
             for (int q = 0; q < 8; q++) x[q] = 0u;
@@ -318,12 +357,12 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
               __syncwarp();
               uint32_t r8[8];  // byte counts: byte q of r8[t] <-> bit q*8 + t of the lane's word
               if (qn <= (uint32_t)G) {  // at most one carrier per sub-group
-                const uint32_t x0 = __ldg(word_ptr(pt_lane, lo.x));
+                const uint32_t x0 = pt_word(lo.x);
 #pragma unroll
                 for (int t = 0; t < 8; t++) r8[t] = (x0 >> t) & 0x01010101u;
               } else {
-                const uint32_t x0 = __ldg(word_ptr(pt_lane, lo.x)), x1 = __ldg(word_ptr(pt_lane, lo.y));
-                const uint32_t x2 = __ldg(word_ptr(pt_lane, lo.z)), x3 = __ldg(word_ptr(pt_lane, lo.w));
+                const uint32_t x0 = pt_word(lo.x), x1 = pt_word(lo.y);
+                const uint32_t x2 = pt_word(lo.z), x3 = pt_word(lo.w);
                 uint32_t c1, s1;
                 csa(c1, s1, x0, x1, x2);
                 const uint32_t q0 = s1 ^ x3, c2 = s1 & x3;
@@ -365,14 +404,14 @@ __global__ void __launch_bounds__(sparse_sc::THREADS, sparse_sc::min_blocks(NW))
             __syncwarp();
             uint32_t x[8];
             const uint4 lo = *reinterpret_cast<const uint4*>(queue + sub * 8), hi = *reinterpret_cast<const uint4*>(queue + sub * 8 + 4);
-            x[0] = __ldg(word_ptr(pt_lane, lo.x));
-            x[1] = __ldg(word_ptr(pt_lane, lo.y));
-            x[2] = __ldg(word_ptr(pt_lane, lo.z));
-            x[3] = __ldg(word_ptr(pt_lane, lo.w));
-            x[4] = __ldg(word_ptr(pt_lane, hi.x));
-            x[5] = __ldg(word_ptr(pt_lane, hi.y));
-            x[6] = __ldg(word_ptr(pt_lane, hi.z));
-            x[7] = __ldg(word_ptr(pt_lane, hi.w));
+            x[0] = pt_word(lo.x);
+            x[1] = pt_word(lo.y);
+            x[2] = pt_word(lo.z);
+            x[3] = pt_word(lo.w);
+            x[4] = pt_word(hi.x);
+            x[5] = pt_word(hi.y);
+            x[6] = pt_word(hi.z);
+            x[7] = pt_word(hi.w);
             const uint32_t rem = qn - real;                      // < 32 entries waiting behind the drained batch
             acc8(c16, pl, inbatch, inreal, x, (int)((real + G - 1) / G), last_chunk && rem == 0);
             // they move to the front: the slot layout is per batch, so whole batches are copied as they are
@@ -548,32 +587,66 @@ static inline bool sparse_sc_applies(const JoinParams& jp, const SparseParams& s
   return sparse_sc_enabled(jp.Ip, sp.n_perm_blocks) && !sp.pcnt1;
 }
 
+// PTS applies to <= 128 permutations when the matrix fits beside the CTA's static shared memory (queues, parked totals:
+// n <= ~12,400) and the launch has enough units to pay for staging it (160 KB per SM, ~10 us); GCRE_SC_PTS=0 / 1 (test hook)
+// forces it off / on where it fits
+static inline bool sparse_sc_pts_wanted(const JoinParams& jp, const SparseParams& sp, int sm_count) {
+  if (jp.Iw != 4 || sparse_wide(sp.n)) return false;
+  if (const char* e = std::getenv("GCRE_SC_PTS")) {
+    if (*e == '0' || *e == '1') return *e == '1';
+  }
+  return sp.n_units >= (unsigned long long)sm_count * (sparse_sc::PTS_THREADS / 32) * 4;
+}
+
 template <int M, bool KEEP, int NW>
-static inline void launch_sparse_sc_ct(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int sm_count) {
+static inline cudaError_t launch_sparse_sc_ct(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int sm_count, bool* pts) {
+  if constexpr (NW == 4) {
+    if (sparse_sc_pts_wanted(jp, sp, sm_count)) {
+      constexpr int warps = sparse_sc::PTS_THREADS / 32;
+      auto kern = join_sparse_sc_kernel<M, KEEP, uint16_t, 4, true>;
+      static int static_smem[64];  // per instantiation and device: static shared memory of the kernel, 0 = not asked yet
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev >= 0 && dev < 64) {
+        if (static_smem[dev] == 0) {
+          cudaFuncAttributes fa;
+          cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+          if (e != cudaSuccess) return e;
+          e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sparse_sc::PTS_SMEM_MAX - fa.sharedSizeBytes));
+          if (e != cudaSuccess) return e;
+          static_smem[dev] = (int)fa.sharedSizeBytes;
+        }
+        const size_t dyn = ((size_t)sp.n + 1) * jp.Iw * 4;
+        if (dyn + (size_t)static_smem[dev] <= sparse_sc::PTS_SMEM_MAX) {
+          const unsigned long long want = (sp.n_units + warps - 1) / warps;
+          const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count);
+          kern<<<grid, sparse_sc::PTS_THREADS, dyn, stream>>>(jp, sp);
+          *pts = true;
+          return cudaGetLastError();
+        }
+      }
+    }
+  }
   const unsigned long long want = (sp.n_units + sparse_sc::WARPS - 1) / sparse_sc::WARPS;
   const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm_count * sparse_sc::min_blocks(NW));
-  if (sparse_wide(sp.n)) join_sparse_sc_kernel<M, KEEP, uint32_t, NW><<<grid, sparse_sc::THREADS, 0, stream>>>(jp, sp);
-  else join_sparse_sc_kernel<M, KEEP, uint16_t, NW><<<grid, sparse_sc::THREADS, 0, stream>>>(jp, sp);
+  if (sparse_wide(sp.n)) join_sparse_sc_kernel<M, KEEP, uint32_t, NW, false><<<grid, sparse_sc::THREADS, 0, stream>>>(jp, sp);
+  else join_sparse_sc_kernel<M, KEEP, uint16_t, NW, false><<<grid, sparse_sc::THREADS, 0, stream>>>(jp, sp);
+  return cudaGetLastError();
 }
 
 template <int M, bool KEEP>
-static inline void launch_sparse_sc_nw(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int sm_count) {
+static inline cudaError_t launch_sparse_sc_nw(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int sm_count, bool* pts) {
   const int nw = sparse_sc_words(jp.Ip);
-  if (nw == 4) launch_sparse_sc_ct<M, KEEP, 4>(stream, jp, sp, sm_count);
-  else if (nw == 8) launch_sparse_sc_ct<M, KEEP, 8>(stream, jp, sp, sm_count);
-  else launch_sparse_sc_ct<M, KEEP, 16>(stream, jp, sp, sm_count);
+  if (nw == 4) return launch_sparse_sc_ct<M, KEEP, 4>(stream, jp, sp, sm_count, pts);
+  if (nw == 8) return launch_sparse_sc_ct<M, KEEP, 8>(stream, jp, sp, sm_count, pts);
+  return launch_sparse_sc_ct<M, KEEP, 16>(stream, jp, sp, sm_count, pts);
 }
 
-static inline cudaError_t launch_join_sparse_sc(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count) {
+// *pts is set when the shared-memory form was launched
+static inline cudaError_t launch_join_sparse_sc(cudaStream_t stream, const JoinParams& jp, const SparseParams& sp, int M, bool keep, int sm_count, bool* pts) {
   if (sp.n_units == 0) return cudaSuccess;
-  if (M == 1) {
-    if (keep) launch_sparse_sc_nw<1, true>(stream, jp, sp, sm_count);
-    else launch_sparse_sc_nw<1, false>(stream, jp, sp, sm_count);
-  } else {
-    if (keep) launch_sparse_sc_nw<2, true>(stream, jp, sp, sm_count);
-    else launch_sparse_sc_nw<2, false>(stream, jp, sp, sm_count);
-  }
-  return cudaGetLastError();
+  if (M == 1) return keep ? launch_sparse_sc_nw<1, true>(stream, jp, sp, sm_count, pts) : launch_sparse_sc_nw<1, false>(stream, jp, sp, sm_count, pts);
+  return keep ? launch_sparse_sc_nw<2, true>(stream, jp, sp, sm_count, pts) : launch_sparse_sc_nw<2, false>(stream, jp, sp, sm_count, pts);
 }
 
 }  // namespace gcre

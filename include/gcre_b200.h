@@ -86,7 +86,7 @@ typedef struct {
   int32_t precounted;       /* out: 1 when the sparse kernel ran in its pre-counted-partner form (join_sparse.cuh) */
   int32_t split_carrier;    /* out: 1 when the <= 512-permutation form of the sparse kernel ran (join_sparse_sc.cuh) */
   int32_t thresholded;      /* out: 1 when the sparse kernel ran with thresholded look-ups (join_sparse.cuh: large method-2 joins) */
-  int32_t reserved;
+  int32_t shared_masks;     /* out: 1 when that form ran with the permutation masks staged in shared memory (<= 128 permutations, small cohorts) */
   uint64_t exact_pairs;     /* out: with thresholded look-ups, the pairs (per 1,024-permutation block) whose exact permutation scores
                                had to be looked up; every other pair was ruled out by one compare per look-up */
   uint64_t reserved2;

@@ -30,11 +30,18 @@ class _Thresholded(_NoSplit):
     (GCRE_THR=1); every other variant forces them off (GCRE_THR=0), so both look-up stages run on every shape."""
 
 
+class _SharedMasks(int):
+    """KERNEL_SPARSE with the split-carrier kernels' shared-memory form (join_sparse_sc.cuh, PTS: the patient-major masks staged
+    in shared memory by a bulk copy, one 1,024-thread CTA per SM) forced onto every join of <= 128 permutations it fits
+    (GCRE_SC_PTS=1); every other variant forces it off, so both forms run on the small shapes."""
+
+
 SPARSE_PC = _Precount(_lib.KERNEL_SPARSE)
 SPARSE_NOSPLIT = _NoSplit(_lib.KERNEL_SPARSE)
 SPARSE_THR = _Thresholded(_lib.KERNEL_SPARSE)
+SPARSE_PTS = _SharedMasks(_lib.KERNEL_SPARSE)
 KERNELS = [pytest.param(_lib.KERNEL_DENSE, id="dense"), pytest.param(_lib.KERNEL_SPARSE, id="sparse"), pytest.param(SPARSE_PC, id="sparse_pc"),
-           pytest.param(SPARSE_NOSPLIT, id="sparse_nosplit"), pytest.param(SPARSE_THR, id="sparse_thr")]
+           pytest.param(SPARSE_NOSPLIT, id="sparse_nosplit"), pytest.param(SPARSE_THR, id="sparse_thr"), pytest.param(SPARSE_PTS, id="sparse_pts")]
 PC_MODES = [pytest.param("0", id="delta"), pytest.param("1", id="precount")]
 
 
@@ -46,6 +53,7 @@ def _precount_mode(request, monkeypatch):
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", "1")
     elif k == _lib.KERNEL_SPARSE:
         monkeypatch.setenv("GCRE_TEST_PRECOUNT", "0")
+    monkeypatch.setenv("GCRE_SC_PTS", "1" if isinstance(k, _SharedMasks) else "0")
     if isinstance(k, _NoSplit):
         monkeypatch.setenv("GCRE_TEST_NO_SPLIT", "1")
     monkeypatch.setenv("GCRE_THR", "1" if isinstance(k, _Thresholded) else "0")
@@ -110,6 +118,8 @@ def test_schedule_matches_oracle(engine, oracles, method, shape, kernel):
             assert got[lvl].info["precounted"] == isinstance(kernel, _Precount), "GCRE_TEST_PRECOUNT must select the kernel form"
         if kernel == _lib.KERNEL_SPARSE and not isinstance(kernel, _Precount) and w.net.levels[lvl].n_pairs > 0:
             assert got[lvl].info["split_carrier"] == (perms <= 512 and not isinstance(kernel, _NoSplit)), "<= 512 permutations run the split-carrier form"
+        if kernel == _lib.KERNEL_SPARSE and w.net.levels[lvl].n_pairs > 0 and got[lvl].info["split_carrier"]:
+            assert got[lvl].info["shared_masks"] == (isinstance(kernel, _SharedMasks) and perms <= 128), "GCRE_SC_PTS must select the shared-memory form"
         if kernel == _lib.KERNEL_SPARSE and w.net.levels[lvl].n_pairs > 0 and not got[lvl].info["split_carrier"]:
             assert got[lvl].info["thresholded"] == isinstance(kernel, _Thresholded), "GCRE_THR must select the look-up stage"
             if isinstance(kernel, _Thresholded):
