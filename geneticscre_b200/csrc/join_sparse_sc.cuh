@@ -35,7 +35,10 @@ constexpr int WARPS = THREADS / 32;
 // PTS form (<= 128 permutations, small cohorts): ONE CTA of 32 warps per SM with the whole patient-major mask matrix
 // ((n + 1) x 16 B) staged in its shared memory by a bulk async copy - the gathers of the hot loop become LDS, and L1 is left
 // to the carrier lists, the upstream rows and the score tables (with the matrix in L1 only a third of the gathers hit).
-constexpr int PTS_THREADS = 1024;
+#ifndef GCRE_SC_PTS_THREADS
+#define GCRE_SC_PTS_THREADS 1024  // measured: 768 threads (80 registers, no spills) +15 % time, 512 threads +50 % - resident warps matter more
+#endif
+constexpr int PTS_THREADS = GCRE_SC_PTS_THREADS;
 constexpr size_t PTS_SMEM_MAX = 232448;  // 227 KB opt-in limit of a CTA on sm_100
 constexpr int QCAP = 128;       // the batch being drained (<= 64 slots) + the < 32 entries that can wait behind it, in whole batches
 constexpr int MAX_PERMS = 512;  // 16 words of 32

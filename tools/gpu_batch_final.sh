@@ -23,6 +23,8 @@ for P in 100 1000 10000; do
   echo "rc=$?" >> $OUT/r2_config5_n1_p$P.err
 done
 python bench.py --n-cases 25000 --n-ctrls 25000 --n-perms 100000 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/r2_config5_n1_p100000.json 2> $OUT/r2_config5_n1_p100000.err
+ncu --metrics $M --clock-control none -k regex:join_ -c 60 --csv --log-file $OUT/r2_counts_cfg3_p100.csv \
+    python bench.py --n-perms 100 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/r2_ncu_counts_cfg3_p100.log 2>&1
 ncu --metrics $M --clock-control none -k regex:join_ -c 60 --csv --log-file $OUT/r2_counts_cfg5_p100.csv \
     python bench.py --n-cases 25000 --n-ctrls 25000 --n-perms 100 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/r2_ncu_counts_cfg5_p100.log 2>&1
 ncu --metrics $M --clock-control none -k regex:join_ -c 60 --csv --log-file $OUT/r2_counts_cfg5_p1000.csv \
