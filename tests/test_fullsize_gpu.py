@@ -75,6 +75,27 @@ def test_row_shards_and_perm_blocks_compose(engine, big):
     assert _key(halves[0])[0] == _key(full)[0] == _key(halves[1])[0]  # the top-K does not depend on the permutations
 
 
+@pytest.mark.parametrize("pts", ["0", "1"])
+@pytest.mark.parametrize("method", ["method1", "method2"])
+def test_few_permutations_are_a_prefix_of_many(engine, big, method, pts, monkeypatch):
+    """A permutation's maximum depends on its own mask only: the first 100 / 256 permutations scored alone - split-carrier
+    kernels (join_sparse_sc.cuh), counts handed from level 3 to level 4 in their layout, masks in shared memory or not - must
+    give the first 100 / 256 maxima of the 1,000-permutation run (1,024-permutation kernels), the same top-K and kept rows."""
+    monkeypatch.setenv("GCRE_SC_PTS", pts)
+    ex, kept, uids = _prepare(engine, big, method, _lib.KERNEL_SPARSE)
+    full = ex.join(uids, kept["paths3"], kept["paths2"], ex.createPathSet(0))
+    assert not full.info["split_carrier"]
+    p3 = kept["paths3"].to_numpy()
+    for n_few in (100, 256):
+        exf, keptf, uidsf = _prepare(engine, big, method, _lib.KERNEL_SPARSE, masks=big.perm_masks[:n_few])
+        few = exf.join(uidsf, keptf["paths3"], keptf["paths2"], exf.createPathSet(0))
+        assert few.info["split_carrier"] and few.info["shared_masks"] == (pts == "1" and n_few <= 128)
+        assert np.array_equal(few.permuted_scores.view(np.uint64), full.permuted_scores[:n_few].view(np.uint64))
+        assert _key(few)[0] == _key(full)[0]
+        assert np.array_equal(keptf["paths3"].to_numpy(), p3)
+        exf.close()
+
+
 @pytest.mark.parametrize("method", ["method1", "method2"])
 def test_first_rows_against_oracle_at_full_width(engine, oracles, big, method):
     ex, kept, _ = _prepare(engine, big, method, _lib.KERNEL_AUTO, top_k=12)

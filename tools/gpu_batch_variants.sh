@@ -1,12 +1,12 @@
 #!/bin/bash
-# split-carrier kernels with the filter loads one chunk ahead: parity, then the 100-permutation step
+# method 2 at <= 128 permutations: both halves of a small pair in one pass - parity, then the 100-permutation step
 set -u
 OUT=gpurun_out
-timeout 600 python -m pytest tests/test_join_gpu.py tests/test_fullsize_gpu.py -m gpu -q -x > $OUT/r2_gputest_pipe.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_gputest_pipe.log
-timeout 300 python bench.py --n-perms 100 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-strong > $OUT/r2_p100_pipe.json 2> $OUT/r2_p100_pipe.err
-GCRE_SC_PTS=0 timeout 300 python bench.py --n-perms 100 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-strong > $OUT/r2_p100_pipe_nopts.json 2> $OUT/r2_p100_pipe_nopts.err
-tail -n 4 $OUT/r2_gputest_pipe.log
-for f in p100_pipe p100_pipe_nopts; do python - $OUT/r2_$f.json <<'PY'
+timeout 900 python -m pytest tests -m gpu -q -x > $OUT/r2_gputest_both.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_gputest_both.log
+timeout 300 python bench.py --n-perms 100 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-strong > $OUT/r2_p100_both.json 2> $OUT/r2_p100_both.err
+timeout 300 python bench.py --n-cases 25000 --n-ctrls 25000 --n-perms 100 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-strong > $OUT/r2_cfg5_p100_both.json 2> $OUT/r2_cfg5_p100_both.err
+tail -n 4 $OUT/r2_gputest_both.log
+for f in p100_both cfg5_p100_both; do python - $OUT/r2_$f.json <<'PY'
 import json,sys
 try:
     d=json.load(open(sys.argv[1]))
