@@ -543,6 +543,8 @@ def roofline_of(last_out, last, w, a, n, ms_step, world):
         alg_bytes += pairs * 2 * W64 * m * 8 + W64 * w.n_perms * 8 + 4 * w.n_perms
         word_ops += pairs * w.n_perms * W64 * m
         kname = {1: "dense", 2: "sparse"}.get(inf["kernel"], "?")
+        if inf.get("split_carrier"):
+            kname = "sparse_sc"  # <= 512 permutations (join_sparse_sc.cuh)
     ker_s = max(ker_ms, 1e-9) * 1e-3
     peaks = load_json("MEASURED_PEAKS.json") or {}
     ip = (load_json("profiles", "r2_int_peak.json") or {}).get("summary", {})
