@@ -14,12 +14,13 @@
 // Everything else - units, filter against the dense upstream row, true scores, candidates with the self-tightening
 // threshold, kept rows - is as in join_sparse.cuh.
 //
-// Per-pair cost is what matters here (a pair brings ~15 new carriers of 4 words), so:
+// Per-pair cost is what matters here (a pair of the bench cohort brings ~32 new carriers of 4 words on average, most pairs far
+// fewer), so:
 //  * a half whose new carriers fit HALF a batch (<= 4 per sub-group: the common case) takes a short path - 1 or 4 gathers per
 //    lane, a 3-plane carry-save sum, BYTE counts and a 7-shuffle reduce-scatter over bytes instead of the 8-gather / 8-plane /
 //    16-register form (about 90 fewer warp instructions per half);
-//  * the true score of a pair (two 64-bit triangle offsets, f64 loads, candidate test) is parked in lane (j mod 32) and worked
-//    off by all lanes at once every 32 pairs instead of by lane 0 behind every pair;
+//  * the totals behind the true score of a pair are parked in shared memory (16 bytes) and the scores of 32 pairs (two 64-bit
+//    triangle offsets, f64 loads, candidate test each) are worked off by 32 lanes at once instead of by lane 0 behind every pair;
 //  * the offsets / lengths of the next partner's lists are loaded one pair ahead;
 //  * KEEP joins emit the counts of the kept rows (R registers per lane and half: 256 B per row and half at <= 128
 //    permutations) with their carrier totals, and the next level takes them as the base of its units: it then needs neither
@@ -34,7 +35,8 @@ constexpr int THREADS = 128;
 constexpr int WARPS = THREADS / 32;
 // PTS form (<= 128 permutations, small cohorts): ONE CTA of 32 warps per SM with the whole patient-major mask matrix
 // ((n + 1) x 16 B) staged in its shared memory by a bulk async copy - the gathers of the hot loop become LDS, and L1 is left
-// to the carrier lists, the upstream rows and the score tables (with the matrix in L1 only a third of the gathers hit).
+// to the carrier lists, the upstream rows and the score tables.  Measured gain 4 % (config 3, 100 permutations): the kernel is
+// bound by its instruction count and the filter's dependent loads, not by these gathers (profiles/r2_sc_full.txt).
 #ifndef GCRE_SC_PTS_THREADS
 #define GCRE_SC_PTS_THREADS 1024  // measured: 768 threads (80 registers, no spills) +15 % time, 512 threads +50 % - resident warps matter more
 #endif
