@@ -76,3 +76,39 @@ def test_host_pack_matches_numpy_packing():
         if cols:
             want = synth.pack_bits((data != 0).astype(np.int32))
             assert np.array_equal(out[:, :w], want[:, :w]), (rows, cols)
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The ctypes structures in geneticscre_b200/_lib.py must have the size and field offsets of the structs include/gcre_b200.h
+    declares (a probe compiled with gcc prints them): a field added on one side only would shift every later field silently."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+
+    from geneticscre_b200 import _lib
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = {"gcre_score": _lib.ScoreC, "gcre_uid_ref": _lib.UidRefC, "gcre_exec_info": _lib.ExecInfoC, "gcre_join_opts": _lib.JoinOptsC,
+             "gcre_decorated": _lib.DecoratedC}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gcre_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, what, val = line.split()
+        cls = pairs[cname]
+        want = C.sizeof(cls) if what == "size" else getattr(cls, what).offset
+        assert int(val) == want, f"{cname}.{what}: header {val}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
