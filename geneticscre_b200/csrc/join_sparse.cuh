@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
   // instruction fetch than to memory latency (profiles/r1_sparse_final_full.txt, no_instruction 4.1 vs long_scoreboard 4.0)
   // method 2: counts parked for the look-up stage.  THR: half 0 only (the last half stays in registers); else both halves
   __shared__ uint32_t s_cnt[(M == 2 && !THR) ? 2 : 1][M == 2 ? 16 : 1][THREADS];
+  __shared__ __align__(16) uint32_t s_park[WARPS][32][2 * M];  // totals of the last <= 32 pairs of the warp's unit (true scores)
 
   const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Wp = a.Wp, Iw = a.Iw;  // Iw: words per patient row of pt (a multiple of 32: every lane owns a valid word)
@@ -715,38 +716,61 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
             }
           }
         }
-        // ---- true score -> top-K candidate (src/methods.h:90-94, 253-264) ----
-        if (lane == 0) {
-          double score;
-          int cases, ctrls;
-          unsigned tmax;
+        // ---- true score -> top-K candidate (src/methods.h:90-94, 253-264): the pair's totals are parked in shared memory and
+        //      the scores of up to 32 pairs are worked off by 32 lanes at once (behind every 32nd pair and the unit's last one)
+        //      instead of by lane 0 behind every pair ----
+        const uint32_t park = (j - j0) & 31u;
+        if (lane == 0) {  // method 1: (carriers, case carriers); method 2: (tp, case_pos, tn, ctrl_pos)
+          if (M == 1) *reinterpret_cast<uint2*>(s_park[warp][park]) = make_uint2(t0[0] + nd[0], nc0[0] + ncn[0]);
+          else *reinterpret_cast<uint4*>(s_park[warp][park]) = make_uint4(t0[0] + nd[0], nc0[0] + ncn[0], t0[M - 1] + nd[M - 1], nc0[M - 1] + ncn[M - 1]);
+        }
+        if (park == 31u || j + 1 == j1) {
+          __syncwarp();
+          const bool mine = (uint32_t)lane <= park;
+          const uint32_t locm = loc - park + (uint32_t)lane;
+          uint32_t pk[2 * M];
           if (M == 1) {
-            cases = (int)(nc0[0] + ncn[0]);
-            tmax = t0[0] + nd[0];
-            ctrls = (int)tmax - cases;
-            score = a.diagD[diag_base(tmax) + cases];
+            const uint2 t = *reinterpret_cast<const uint2*>(s_park[warp][lane]);
+            pk[0] = t.x; pk[1] = t.y;
           } else {
-            const unsigned tp = t0[0] + nd[0], tn = t0[M - 1] + nd[M - 1];
-            const unsigned case_pos = nc0[0] + ncn[0], ctrl_neg = tp - case_pos;
-            const unsigned ctrl_pos = nc0[M - 1] + ncn[M - 1], case_neg = tn - ctrl_pos;
-            score = a.diagD[diag_base(tp) + case_pos] + a.diagD[diag_base(tn) + case_neg];
-            cases = (int)(case_pos + case_neg);
-            ctrls = (int)(ctrl_pos + ctrl_neg);
-            tmax = max(tp, tn);
+            const uint4 t = *reinterpret_cast<const uint4*>(s_park[warp][lane]);
+            pk[0] = t.x; pk[1] = t.y; pk[2 * M - 2] = t.z; pk[2 * M - 1] = t.w;
           }
-          if (KEEP) atomicMax(a.max_total, tmax);
-          if (score == score) {
+          double score = 0.0;
+          int cases = 0, ctrls = 0;
+          unsigned tmax = 0;
+          if (mine) {
+            if (M == 1) {
+              cases = (int)pk[1];
+              tmax = pk[0];
+              ctrls = (int)tmax - cases;
+              score = a.diagD[diag_base(tmax) + cases];
+            } else {
+              const unsigned tp = pk[0], tn = pk[2 * M - 2];
+              const unsigned case_pos = pk[1], ctrl_neg = tp - case_pos;
+              const unsigned ctrl_pos = pk[2 * M - 1], case_neg = tn - ctrl_pos;
+              score = a.diagD[diag_base(tp) + case_pos] + a.diagD[diag_base(tn) + case_neg];
+              cases = (int)(case_pos + case_neg);
+              ctrls = (int)(ctrl_pos + ctrl_neg);
+              tmax = max(tp, tn);
+            }
+          }
+          if (KEEP) {
+            const unsigned m = __reduce_max_sync(0xffffffffu, tmax);
+            if (lane == 0) atomicMax(a.max_total, m);
+          }
+          if (mine && score == score) {
             const unsigned long long key = score_key(score);
-            const unsigned long long dyn = a.n_slots ? __ldcg(a.dyn_thr) : 0ull;  // (read here, by lane 0 only: no register held across the pair)
+            const unsigned long long dyn = a.n_slots ? __ldcg(a.dyn_thr) : 0ull;
             if (key > a.thr_key && key >= dyn) {
               const unsigned slot = atomicAdd(a.cand_count, 1u);
               if (slot < a.cand_cap) {
                 Cand cd;
-                cd.key = key; cd.idx = idx; cd.loc = loc; cd.cases = cases; cd.ctrls = ctrls;
+                cd.key = key; cd.idx = idx; cd.loc = locm; cd.cases = cases; cd.ctrls = ctrls;
                 a.cand[slot] = cd;
               }
               if (a.n_slots) {
-                const unsigned bucket = ((idx * 0x9E3779B1u) ^ (loc * 0x85EBCA6Bu)) >> 8;
+                const unsigned bucket = ((idx * 0x9E3779B1u) ^ (locm * 0x85EBCA6Bu)) >> 8;
                 if (atomicMax(a.slots + bucket % (unsigned)a.n_slots, key) < key) {
                   unsigned long long m = ~0ull;
                   for (int t = 0; t < a.n_slots; t++) m = min(m, __ldcg(a.slots + t));
@@ -755,6 +779,7 @@ __global__ void __launch_bounds__(sparse::THREADS, sparse::min_blocks(M, THR)) j
               }
             }
           }
+          __syncwarp();
         }
       }
     }
