@@ -1,6 +1,7 @@
 #!/bin/bash
-# the default bench line once more, now that profiles/r2_counts.json holds the instruction counts of the final kernels
+# Round-end check of the committed tree on one B200: the whole GPU test suite and smoke()
 set -u
 OUT=gpurun_out
-python bench.py --steps 20 --warmup 5 > $OUT/r2_bench_n1.json 2> $OUT/r2_bench_n1.err; echo "rc=$?" >> $OUT/r2_bench_n1.err
-tail -n 2 $OUT/r2_bench_n1.err
+python -m pytest tests -x -q -m gpu > $OUT/r2_head_gputest.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_head_gputest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $OUT/r2_head_smoke.log 2>&1; echo "rc=$?" >> $OUT/r2_head_smoke.log
+tail -n 3 $OUT/r2_head_gputest.log; tail -n 3 $OUT/r2_head_smoke.log
