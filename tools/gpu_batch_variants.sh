@@ -1,7 +1,6 @@
 #!/bin/bash
-# Round-end check of the committed tree on one B200: the whole GPU test suite and smoke()
+# quick check of the adaptive end-to-end warm-up in bench.py
 set -u
 OUT=gpurun_out
-python -m pytest tests -x -q -m gpu > $OUT/r2_head_gputest.log 2>&1; echo "pytest rc=$?" >> $OUT/r2_head_gputest.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $OUT/r2_head_smoke.log 2>&1; echo "rc=$?" >> $OUT/r2_head_smoke.log
-tail -n 3 $OUT/r2_head_gputest.log; tail -n 3 $OUT/r2_head_smoke.log
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-strong --e2e-steps 10 > $OUT/r2_e2e_adaptive.json 2> $OUT/r2_e2e_adaptive.err; echo "rc=$?" >> $OUT/r2_e2e_adaptive.err
+tail -n 2 $OUT/r2_e2e_adaptive.err
